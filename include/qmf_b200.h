@@ -1,0 +1,109 @@
+/* qmf_b200 — C ABI of the B200-native (sm_100a) replacement for the training hot path of
+ * taozhijiang/qmf.  Plain pointers and sizes only; no C++/torch types.  All functions return 0 on
+ * success or a negative QMFB_ERR_* code; qmfb_last_error() describes the last failure of the
+ * calling thread.  The reference has no FFI of its own (single C++ process); each entry point
+ * below cites the reference function whose inner loop it replaces, and INTEGRATION.md shows the
+ * call a maintainer would add at that site.
+ *
+ * Two levels:
+ *   qmfb_*_dev   kernel level: the caller owns device memory and the CUDA stream (used by the
+ *                one-process-per-GPU driver that does its exchange steps with NCCL).
+ *   qmfb_wals_* / qmfb_bpr_* / qmfb_eval_*   engine level: host buffers in, host buffers out;
+ *                the library owns device memory.  This is what the C++ engines
+ *                (qmf_b200/host/qmf/...) bind.
+ *
+ * Device layout: a factor matrix with k factors is stored row-major with row stride
+ * KP = qmfb_padded_k(k) doubles (k rounded up to 32/64/96/128), pad columns are zero.
+ */
+#ifndef QMF_B200_H
+#define QMF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMFB_OK 0
+#define QMFB_ERR_INVALID (-1)    /* bad argument */
+#define QMFB_ERR_CUDA (-2)       /* CUDA runtime failure (no device, launch failure, ...) */
+#define QMFB_ERR_NOT_SPD (-3)    /* a row's normal equations were not positive definite; mirrors
+                                    CHECK_EQ(result, 0) after dsysv_, qmf/Matrix.cpp:94 */
+#define QMFB_ERR_NOT_FINITE (-4) /* non-finite BPR gradient; mirrors CHECK(std::isfinite(e)),
+                                    qmf/bpr/BPREngine.cpp:184-185 */
+#define QMFB_ERR_UNSUPPORTED (-5)
+
+#define QMFB_SIDE_USER 0
+#define QMFB_SIDE_ITEM 1
+
+const char* qmfb_last_error(void);
+int qmfb_version(void);
+/* number of CUDA devices visible, or a negative error */
+int qmfb_device_count(void);
+
+/* ---------------------------------------------------------------- layout helpers ---------- */
+int qmfb_padded_k(int k);                 /* KP; negative if k is unsupported (k < 1 or k > 128) */
+int64_t qmfb_gram_packed_len(int k);      /* doubles in the packed upper-tile Gram of KP x KP */
+int64_t qmfb_gram_workspace_len(int k);   /* doubles of scratch qmfb_gram_dev needs */
+
+/* ---------------------------------------------------------------- kernel level (device) ---- */
+/* Partial Gram G = sum_{r in [row_begin,row_end)} y_r y_r^T in packed upper-tile form
+ * (replaces WALSEngine::computeXtX, qmf/wals/WALSEngine.cpp:246-264).  Deterministic.  Partial
+ * results of several ranks are combined by summing gram_packed element-wise (NCCL allreduce). */
+int qmfb_gram_dev(void* stream, const double* Y, int64_t ldy, int64_t row_begin, int64_t row_end, int k,
+                  double* workspace, double* gram_packed);
+/* packed upper tiles -> dense symmetric k x k row-major */
+int qmfb_gram_unpack_dev(void* stream, const double* gram_packed, int k, double* out);
+/* Solve `nrows` rows of one half-step (replaces the per-row body of WALSEngine::iterate,
+ * qmf/wals/WALSEngine.cpp:205-214 -> updateFactorsForOne :266-310 -> dsysv_ Matrix.cpp:92):
+ *   A = G + sum_s alpha r_s y_s y_s^T + lambda I,  b = sum_s (1 + alpha r_s) y_s,  x = A^{-1} b,
+ *   row_loss = sum_s (1 + alpha r_s) + x^T (A - lambda I) x - 2 x^T b.
+ * CSR arrays are local to the shard (row_ptr[0] == 0); X row written = row_offset + local row.
+ * `order` lists local rows longest-first (any permutation is valid).  `scratch` is 2 ints
+ * (scheduler counter, error flag; the call resets both).  loss_sum (device, 1 double) receives
+ * the deterministic sum of row_loss.  Asynchronous on `stream`. */
+int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset, const double* Y, int64_t ldy, int k,
+                        const int64_t* row_ptr, const int32_t* col, const double* val, const int32_t* order,
+                        int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
+                        double* loss_sum, int32_t* scratch);
+
+/* ---------------------------------------------------------------- WALS engine (host) ------- */
+typedef struct qmfb_wals qmfb_wals_t;
+/* One handle per process/GPU.  nusers x nitems problem with `nfactors` factors; both factor
+ * matrices are resident (zero-initialised) on `device`. */
+int qmfb_wals_create(int device, int64_t nusers, int64_t nitems, int nfactors, qmfb_wals_t** out);
+int qmfb_wals_destroy(qmfb_wals_t* h);
+/* Upload the CSR of one orientation (side USER: user rows over item idx; side ITEM: item rows
+ * over user idx), as built by WALSEngine::groupSignals (qmf/wals/WALSEngine.cpp:130-154): rows in
+ * ascending raw-id order, entries in ascending raw-id order, duplicates kept.  The shard
+ * [row_begin, row_begin + nrows) is what this handle solves; row_ptr has nrows+1 entries
+ * starting at 0. */
+int qmfb_wals_set_csr(qmfb_wals_t* h, int side, int64_t row_begin, int64_t nrows, const int64_t* row_ptr,
+                      const int32_t* col_idx, const double* val);
+/* host (n x nfactors row-major, the layout of qmf::Matrix, qmf/Matrix.h:79-81) <-> device */
+int qmfb_wals_set_factors(qmfb_wals_t* h, int side, const double* host);
+int qmfb_wals_get_factors(qmfb_wals_t* h, int side, double* host);
+/* Gram of one side's factors, dense nfactors x nfactors row-major on the host */
+int qmfb_wals_gram(qmfb_wals_t* h, int side, double* host_out);
+/* One half-step over this handle's shard of `update_side` (WALSEngine::iterate,
+ * qmf/wals/WALSEngine.cpp:165-218): zero the side, Gram of the other side, solve every row.
+ * *loss_sum receives sum of row losses (NOT yet divided by nusers*nitems). */
+int qmfb_wals_half_step(qmfb_wals_t* h, int update_side, double alpha, double lambda, double* loss_sum);
+/* One epoch through HOST buffers (WALSEngine::optimize loop body, WALSEngine.cpp:86-92):
+ * uploads item factors, runs the user then the item half-step, downloads both factor matrices
+ * and returns the item-step loss divided by nusers*nitems, exactly what the reference logs. */
+int qmfb_wals_epoch_host(qmfb_wals_t* h, double alpha, double lambda, const double* item_factors_in,
+                         double* user_factors_out, double* item_factors_out, double* loss_out);
+/* device-side views for multi-GPU drivers (row stride = qmfb_padded_k(nfactors)) */
+double* qmfb_wals_factors_device(qmfb_wals_t* h, int side);
+void* qmfb_wals_stream(qmfb_wals_t* h);
+/* number of kernels launched by this handle so far */
+int64_t qmfb_wals_launch_count(qmfb_wals_t* h);
+/* device milliseconds (CUDA events on the handle's stream) spent in the last half-step's Gram
+ * and row-solve kernels */
+int qmfb_wals_last_timing(qmfb_wals_t* h, float* gram_ms, float* solve_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMF_B200_H */

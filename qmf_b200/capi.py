@@ -1,0 +1,77 @@
+"""ctypes binding of the C ABI in include/qmf_b200.h (libqmf_b200.so, built in-tree by
+qmf_b200/csrc/Makefile).  There is NO CPU fallback: if the library is missing, import fails
+loudly; if a call fails, :class:`QmfbError` carries qmfb_last_error()."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqmf_b200.so")
+
+SIDE_USER = 0
+SIDE_ITEM = 1
+ERR_NOT_SPD = -3
+ERR_NOT_FINITE = -4
+
+
+class QmfbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("qmf_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "qmf_b200: %s is missing — build it with `make -C qmf_b200/csrc` (or __graft_entry__.build()); "
+        "there is no CPU fallback" % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+c_i64 = C.c_int64
+c_f64 = C.c_double
+vp = C.c_void_p
+p_i64 = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+p_i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+p_f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+_SIG = {
+    "qmfb_last_error": (C.c_char_p, []),
+    "qmfb_version": (C.c_int, []),
+    "qmfb_device_count": (C.c_int, []),
+    "qmfb_padded_k": (C.c_int, [C.c_int]),
+    "qmfb_gram_packed_len": (c_i64, [C.c_int]),
+    "qmfb_gram_workspace_len": (c_i64, [C.c_int]),
+    "qmfb_gram_dev": (C.c_int, [vp, vp, c_i64, c_i64, c_i64, C.c_int, vp, vp]),
+    "qmfb_gram_unpack_dev": (C.c_int, [vp, vp, C.c_int, vp]),
+    "qmfb_wals_solve_dev": (C.c_int, [vp, vp, c_i64, c_i64, vp, c_i64, C.c_int, vp, vp, vp, vp, c_i64, vp, c_f64, c_f64,
+                                      vp, vp, vp]),
+    "qmfb_wals_create": (C.c_int, [C.c_int, c_i64, c_i64, C.c_int, C.POINTER(vp)]),
+    "qmfb_wals_destroy": (C.c_int, [vp]),
+    "qmfb_wals_set_csr": (C.c_int, [vp, C.c_int, c_i64, c_i64, p_i64, p_i32, p_f64]),
+    "qmfb_wals_set_factors": (C.c_int, [vp, C.c_int, p_f64]),
+    "qmfb_wals_get_factors": (C.c_int, [vp, C.c_int, p_f64]),
+    "qmfb_wals_gram": (C.c_int, [vp, C.c_int, p_f64]),
+    "qmfb_wals_half_step": (C.c_int, [vp, C.c_int, c_f64, c_f64, C.POINTER(c_f64)]),
+    "qmfb_wals_epoch_host": (C.c_int, [vp, c_f64, c_f64, vp, vp, vp, C.POINTER(c_f64)]),
+    "qmfb_wals_factors_device": (vp, [vp, C.c_int]),
+    "qmfb_wals_stream": (vp, [vp]),
+    "qmfb_wals_launch_count": (c_i64, [vp]),
+    "qmfb_wals_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+}
+
+EXPORTS = tuple(_SIG)
+for _name, (_res, _args) in _SIG.items():
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+def last_error():
+    return lib.qmfb_last_error().decode()
+
+
+def check(rc):
+    if rc < 0:
+        raise QmfbError(rc, last_error())
+    return rc

@@ -1,0 +1,372 @@
+// C-ABI (include/qmf_b200.h) for the WALS half-step: launchers + the host-buffer engine handle.
+#include "qmfb_common.h"
+#include "wals_kernels.cuh"
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+namespace qmfb {
+
+constexpr int kGramMaxParts = 296;  // 2 CTAs per SM on a 148-SM B200
+
+template <int NT>
+static int launch_gram(cudaStream_t st, const double* Y, int64_t ldy, int64_t r0, int64_t r1, int k, double* ws,
+                       double* packed) {
+  using SM = WalsSmem<NT>;
+  static bool configured = false;
+  if (!configured) {
+    QMFB_CUDA(cudaFuncSetAttribute(gram_partial_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+    configured = true;
+  }
+  const int64_t n = r1 - r0;
+  int parts = int(std::min<int64_t>(kGramMaxParts, std::max<int64_t>(1, (n + 4 * kChunk - 1) / (4 * kChunk))));
+  gram_partial_kernel<NT><<<parts, SM::NTHREADS, SM::kBytes, st>>>(Y, ldy, r0, r1, ws);
+  QMFB_CUDA(cudaGetLastError());
+  const int nelem = SM::NTILE_A * 64;
+  gram_reduce_kernel<<<(nelem + 255) / 256, 256, 0, st>>>(ws, parts, nelem, packed);
+  QMFB_CUDA(cudaGetLastError());
+  (void)k;
+  return QMFB_OK;
+}
+
+template <int NT>
+static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_sum, int32_t* scratch) {
+  using SM = WalsSmem<NT>;
+  static int grid_cap = 0;
+  if (grid_cap == 0) {
+    QMFB_CUDA(cudaFuncSetAttribute(wals_solve_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+    int dev = 0, sms = 0, occ = 0;
+    QMFB_CUDA(cudaGetDevice(&dev));
+    QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    QMFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wals_solve_kernel<NT>, SM::NTHREADS, SM::kBytes));
+    if (occ < 1) return set_error(QMFB_ERR_CUDA, "wals_solve_kernel does not fit on an SM");
+    grid_cap = sms * occ;
+  }
+  QMFB_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(int32_t), st));
+  if (prm.nrows > 0) {
+    const int grid = int(std::min<int64_t>(grid_cap, prm.nrows));
+    wals_solve_kernel<NT><<<grid, SM::NTHREADS, SM::kBytes, st>>>(prm);
+    QMFB_CUDA(cudaGetLastError());
+  }
+  sum_kernel<<<1, 1024, 0, st>>>(prm.row_loss, prm.nrows, loss_sum);
+  QMFB_CUDA(cudaGetLastError());
+  return QMFB_OK;
+}
+
+}  // namespace qmfb
+
+using namespace qmfb;
+
+extern "C" {
+
+int qmfb_padded_k(int k) {
+  if (k < 1 || k > 128) return set_error(QMFB_ERR_UNSUPPORTED, "nfactors must be in [1, 128] (got %d)", k);
+  return ((k + 31) / 32) * 32;
+}
+
+int64_t qmfb_gram_packed_len(int k) {
+  const int kp = qmfb_padded_k(k);
+  if (kp < 0) return kp;
+  const int nt = kp / 8;
+  return int64_t(nt) * (nt + 1) / 2 * 64;
+}
+
+int64_t qmfb_gram_workspace_len(int k) {
+  const int64_t n = qmfb_gram_packed_len(k);
+  return n < 0 ? n : n * kGramMaxParts;
+}
+
+int qmfb_gram_dev(void* stream, const double* Y, int64_t ldy, int64_t row_begin, int64_t row_end, int k,
+                  double* workspace, double* gram_packed) {
+  const int kp = qmfb_padded_k(k);
+  if (kp < 0) return kp;
+  if (ldy < kp || row_end < row_begin || !Y || !workspace || !gram_packed) return set_error(QMFB_ERR_INVALID, "qmfb_gram_dev: bad argument");
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (kp / 8) {
+    case 4: return launch_gram<4>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
+    case 8: return launch_gram<8>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
+    case 12: return launch_gram<12>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
+    case 16: return launch_gram<16>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
+  }
+  return set_error(QMFB_ERR_UNSUPPORTED, "unsupported padded k %d", kp);
+}
+
+int qmfb_gram_unpack_dev(void* stream, const double* gram_packed, int k, double* out) {
+  const int kp = qmfb_padded_k(k);
+  if (kp < 0) return kp;
+  auto st = static_cast<cudaStream_t>(stream);
+  const int nb = (k * k + 255) / 256;
+  switch (kp / 8) {
+    case 4: gram_unpack_kernel<4><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
+    case 8: gram_unpack_kernel<8><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
+    case 12: gram_unpack_kernel<12><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
+    case 16: gram_unpack_kernel<16><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
+  }
+  QMFB_CUDA(cudaGetLastError());
+  return QMFB_OK;
+}
+
+int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset, const double* Y, int64_t ldy, int k,
+                        const int64_t* row_ptr, const int32_t* col, const double* val, const int32_t* order,
+                        int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
+                        double* loss_sum, int32_t* scratch) {
+  const int kp = qmfb_padded_k(k);
+  if (kp < 0) return kp;
+  if (ldx < kp || ldy < kp || nrows < 0 || nrows > INT32_MAX || !X || !Y || !row_ptr || !order || !gram_packed || !row_loss ||
+      !loss_sum || !scratch) {
+    return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_dev: bad argument");
+  }
+  SolveParams prm{X, ldx, row_offset, Y, ldy, k, row_ptr, col, val, order, int(nrows), gram_packed, alpha, lambda,
+                  row_loss, scratch, scratch + 1};
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (kp / 8) {
+    case 4: return launch_solve<4>(st, prm, loss_sum, scratch);
+    case 8: return launch_solve<8>(st, prm, loss_sum, scratch);
+    case 12: return launch_solve<12>(st, prm, loss_sum, scratch);
+    case 16: return launch_solve<16>(st, prm, loss_sum, scratch);
+  }
+  return set_error(QMFB_ERR_UNSUPPORTED, "unsupported padded k %d", kp);
+}
+
+// ------------------------------------------------------------------------------------------
+// engine level
+// ------------------------------------------------------------------------------------------
+struct qmfb_wals {
+  int device = 0;
+  int64_t n[2] = {0, 0};
+  int k = 0, kp = 0;
+  cudaStream_t stream = nullptr;
+  double* F[2] = {nullptr, nullptr};
+  int64_t row_begin[2] = {0, 0}, nrows[2] = {0, 0}, nnz[2] = {0, 0};
+  int64_t* row_ptr[2] = {nullptr, nullptr};
+  int32_t* col[2] = {nullptr, nullptr};
+  double* val[2] = {nullptr, nullptr};
+  int32_t* order[2] = {nullptr, nullptr};
+  double *gram_ws = nullptr, *gram_packed = nullptr, *gram_full = nullptr, *row_loss = nullptr, *loss_sum = nullptr;
+  int32_t* scratch = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  float gram_ms = 0.f, solve_ms = 0.f;
+  int64_t launches = 0;
+};
+
+static int wals_release(qmfb_wals* h) {
+  cudaSetDevice(h->device);
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(h->F[s]);
+    cudaFree(h->row_ptr[s]);
+    cudaFree(h->col[s]);
+    cudaFree(h->val[s]);
+    cudaFree(h->order[s]);
+  }
+  cudaFree(h->gram_ws);
+  cudaFree(h->gram_packed);
+  cudaFree(h->gram_full);
+  cudaFree(h->row_loss);
+  cudaFree(h->loss_sum);
+  cudaFree(h->scratch);
+  for (auto& e : h->ev) {
+    if (e) cudaEventDestroy(e);
+  }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return QMFB_OK;
+}
+
+int qmfb_wals_create(int device, int64_t nusers, int64_t nitems, int nfactors, qmfb_wals_t** out) {
+  if (!out || nusers < 1 || nitems < 1) return set_error(QMFB_ERR_INVALID, "qmfb_wals_create: bad argument");
+  const int kp = qmfb_padded_k(nfactors);
+  if (kp < 0) return kp;
+  QMFB_CUDA(cudaSetDevice(device));
+  auto* h = new qmfb_wals;
+  h->device = device;
+  h->n[0] = nusers;
+  h->n[1] = nitems;
+  h->k = nfactors;
+  h->kp = kp;
+  int rc = [&]() -> int {
+    QMFB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+      QMFB_CUDA(cudaMalloc(&h->F[s], size_t(h->n[s]) * kp * sizeof(double)));
+      QMFB_CUDA(cudaMemsetAsync(h->F[s], 0, size_t(h->n[s]) * kp * sizeof(double), h->stream));
+    }
+    QMFB_CUDA(cudaMalloc(&h->gram_ws, size_t(qmfb_gram_workspace_len(nfactors)) * sizeof(double)));
+    QMFB_CUDA(cudaMalloc(&h->gram_packed, size_t(qmfb_gram_packed_len(nfactors)) * sizeof(double)));
+    QMFB_CUDA(cudaMalloc(&h->gram_full, size_t(nfactors) * nfactors * sizeof(double)));
+    QMFB_CUDA(cudaMalloc(&h->row_loss, size_t(std::max(nusers, nitems)) * sizeof(double)));
+    QMFB_CUDA(cudaMalloc(&h->loss_sum, sizeof(double)));
+    QMFB_CUDA(cudaMalloc(&h->scratch, 2 * sizeof(int32_t)));
+    for (auto& e : h->ev) QMFB_CUDA(cudaEventCreate(&e));
+    QMFB_CUDA(cudaStreamSynchronize(h->stream));
+    return QMFB_OK;
+  }();
+  if (rc != QMFB_OK) {
+    wals_release(h);
+    return rc;
+  }
+  *out = h;
+  return QMFB_OK;
+}
+
+int qmfb_wals_destroy(qmfb_wals_t* h) {
+  if (!h) return QMFB_OK;
+  return wals_release(h);
+}
+
+int qmfb_wals_set_csr(qmfb_wals_t* h, int side, int64_t row_begin, int64_t nrows, const int64_t* row_ptr,
+                      const int32_t* col_idx, const double* val) {
+  if (!h || side < 0 || side > 1 || !row_ptr || nrows < 0 || row_begin < 0 || row_begin + nrows > h->n[side] || row_ptr[0] != 0) {
+    return set_error(QMFB_ERR_INVALID, "qmfb_wals_set_csr: bad argument");
+  }
+  const int64_t nnz = row_ptr[nrows];
+  if (nnz > 0 && (!col_idx || !val)) return set_error(QMFB_ERR_INVALID, "qmfb_wals_set_csr: null col/val");
+  const int64_t ncols = h->n[1 - side];
+  for (int64_t r = 0; r < nrows; ++r) {
+    if (row_ptr[r + 1] < row_ptr[r]) return set_error(QMFB_ERR_INVALID, "qmfb_wals_set_csr: row_ptr not monotone at %lld", (long long)r);
+  }
+  for (int64_t p = 0; p < nnz; ++p) {
+    if (col_idx[p] < 0 || col_idx[p] >= ncols) return set_error(QMFB_ERR_INVALID, "qmfb_wals_set_csr: col_idx[%lld]=%d out of range", (long long)p, col_idx[p]);
+  }
+  QMFB_CUDA(cudaSetDevice(h->device));
+  cudaFree(h->row_ptr[side]);
+  cudaFree(h->col[side]);
+  cudaFree(h->val[side]);
+  cudaFree(h->order[side]);
+  h->row_ptr[side] = nullptr; h->col[side] = nullptr; h->val[side] = nullptr; h->order[side] = nullptr;
+  // longest rows first: the persistent solve kernel pulls rows through an atomic counter
+  std::vector<int32_t> order(static_cast<size_t>(nrows));
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [row_ptr](int32_t a, int32_t b) {
+    return row_ptr[a + 1] - row_ptr[a] > row_ptr[b + 1] - row_ptr[b];
+  });
+  QMFB_CUDA(cudaMalloc(&h->row_ptr[side], size_t(nrows + 1) * sizeof(int64_t)));
+  QMFB_CUDA(cudaMalloc(&h->col[side], size_t(std::max<int64_t>(nnz, 1)) * sizeof(int32_t)));
+  QMFB_CUDA(cudaMalloc(&h->val[side], size_t(std::max<int64_t>(nnz, 1)) * sizeof(double)));
+  QMFB_CUDA(cudaMalloc(&h->order[side], size_t(std::max<int64_t>(nrows, 1)) * sizeof(int32_t)));
+  QMFB_CUDA(cudaMemcpyAsync(h->row_ptr[side], row_ptr, size_t(nrows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  if (nnz > 0) {
+    QMFB_CUDA(cudaMemcpyAsync(h->col[side], col_idx, size_t(nnz) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    QMFB_CUDA(cudaMemcpyAsync(h->val[side], val, size_t(nnz) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (nrows > 0) {
+    QMFB_CUDA(cudaMemcpyAsync(h->order[side], order.data(), size_t(nrows) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  }
+  QMFB_CUDA(cudaStreamSynchronize(h->stream));
+  h->row_begin[side] = row_begin;
+  h->nrows[side] = nrows;
+  h->nnz[side] = nnz;
+  return QMFB_OK;
+}
+
+int qmfb_wals_set_factors(qmfb_wals_t* h, int side, const double* host) {
+  if (!h || side < 0 || side > 1 || !host) return set_error(QMFB_ERR_INVALID, "qmfb_wals_set_factors: bad argument");
+  QMFB_CUDA(cudaSetDevice(h->device));
+  QMFB_CUDA(cudaMemcpy2DAsync(h->F[side], size_t(h->kp) * 8, host, size_t(h->k) * 8, size_t(h->k) * 8, size_t(h->n[side]),
+                              cudaMemcpyHostToDevice, h->stream));
+  QMFB_CUDA(cudaStreamSynchronize(h->stream));
+  return QMFB_OK;
+}
+
+int qmfb_wals_get_factors(qmfb_wals_t* h, int side, double* host) {
+  if (!h || side < 0 || side > 1 || !host) return set_error(QMFB_ERR_INVALID, "qmfb_wals_get_factors: bad argument");
+  QMFB_CUDA(cudaSetDevice(h->device));
+  QMFB_CUDA(cudaMemcpy2DAsync(host, size_t(h->k) * 8, h->F[side], size_t(h->kp) * 8, size_t(h->k) * 8, size_t(h->n[side]),
+                              cudaMemcpyDeviceToHost, h->stream));
+  QMFB_CUDA(cudaStreamSynchronize(h->stream));
+  return QMFB_OK;
+}
+
+int qmfb_wals_gram(qmfb_wals_t* h, int side, double* host_out) {
+  if (!h || side < 0 || side > 1 || !host_out) return set_error(QMFB_ERR_INVALID, "qmfb_wals_gram: bad argument");
+  QMFB_CUDA(cudaSetDevice(h->device));
+  int rc = qmfb_gram_dev(h->stream, h->F[side], h->kp, 0, h->n[side], h->k, h->gram_ws, h->gram_packed);
+  if (rc) return rc;
+  rc = qmfb_gram_unpack_dev(h->stream, h->gram_packed, h->k, h->gram_full);
+  if (rc) return rc;
+  h->launches += 3;
+  QMFB_CUDA(cudaMemcpyAsync(host_out, h->gram_full, size_t(h->k) * h->k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  QMFB_CUDA(cudaStreamSynchronize(h->stream));
+  return QMFB_OK;
+}
+
+static int wals_half_step_async(qmfb_wals* h, int side, double alpha, double lambda) {
+  const int other = 1 - side;
+  if (!h->row_ptr[side]) return set_error(QMFB_ERR_INVALID, "qmfb_wals_half_step: no CSR uploaded for side %d", side);
+  // leftData.setFactors(0), WALSEngine.cpp:170-171 (this shard's rows)
+  QMFB_CUDA(cudaMemsetAsync(h->F[side] + h->row_begin[side] * h->kp, 0, size_t(h->nrows[side]) * h->kp * sizeof(double), h->stream));
+  QMFB_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  int rc = qmfb_gram_dev(h->stream, h->F[other], h->kp, 0, h->n[other], h->k, h->gram_ws, h->gram_packed);
+  if (rc) return rc;
+  QMFB_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  rc = qmfb_wals_solve_dev(h->stream, h->F[side], h->kp, h->row_begin[side], h->F[other], h->kp, h->k, h->row_ptr[side],
+                           h->col[side], h->val[side], h->order[side], h->nrows[side], h->gram_packed, alpha, lambda,
+                           h->row_loss, h->loss_sum, h->scratch);
+  if (rc) return rc;
+  QMFB_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  h->launches += 4;
+  return QMFB_OK;
+}
+
+static int wals_finish_step(qmfb_wals* h, double* loss_sum) {
+  double loss = 0.0;
+  int32_t scratch[2] = {0, 0};
+  QMFB_CUDA(cudaMemcpyAsync(&loss, h->loss_sum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  QMFB_CUDA(cudaMemcpyAsync(scratch, h->scratch, sizeof(scratch), cudaMemcpyDeviceToHost, h->stream));
+  QMFB_CUDA(cudaStreamSynchronize(h->stream));
+  QMFB_CUDA(cudaEventElapsedTime(&h->gram_ms, h->ev[0], h->ev[1]));
+  QMFB_CUDA(cudaEventElapsedTime(&h->solve_ms, h->ev[1], h->ev[2]));
+  if (scratch[1] != 0) return set_error(QMFB_ERR_NOT_SPD, "normal equations not positive definite (reference: dsysv failed)");
+  if (loss_sum) *loss_sum = loss;
+  return QMFB_OK;
+}
+
+int qmfb_wals_half_step(qmfb_wals_t* h, int update_side, double alpha, double lambda, double* loss_sum) {
+  if (!h || update_side < 0 || update_side > 1) return set_error(QMFB_ERR_INVALID, "qmfb_wals_half_step: bad argument");
+  QMFB_CUDA(cudaSetDevice(h->device));
+  int rc = wals_half_step_async(h, update_side, alpha, lambda);
+  if (rc) return rc;
+  return wals_finish_step(h, loss_sum);
+}
+
+int qmfb_wals_epoch_host(qmfb_wals_t* h, double alpha, double lambda, const double* item_factors_in,
+                         double* user_factors_out, double* item_factors_out, double* loss_out) {
+  if (!h) return set_error(QMFB_ERR_INVALID, "qmfb_wals_epoch_host: null handle");
+  QMFB_CUDA(cudaSetDevice(h->device));
+  if (item_factors_in) {
+    QMFB_CUDA(cudaMemcpy2DAsync(h->F[1], size_t(h->kp) * 8, item_factors_in, size_t(h->k) * 8, size_t(h->k) * 8,
+                                size_t(h->n[1]), cudaMemcpyHostToDevice, h->stream));
+  }
+  int rc = wals_half_step_async(h, QMFB_SIDE_USER, alpha, lambda);
+  if (rc) return rc;
+  int32_t err_user[2] = {0, 0};
+  QMFB_CUDA(cudaMemcpyAsync(err_user, h->scratch, sizeof(err_user), cudaMemcpyDeviceToHost, h->stream));
+  if (user_factors_out) {
+    QMFB_CUDA(cudaMemcpy2DAsync(user_factors_out, size_t(h->k) * 8, h->F[0], size_t(h->kp) * 8, size_t(h->k) * 8,
+                                size_t(h->n[0]), cudaMemcpyDeviceToHost, h->stream));
+  }
+  rc = wals_half_step_async(h, QMFB_SIDE_ITEM, alpha, lambda);
+  if (rc) return rc;
+  if (item_factors_out) {
+    QMFB_CUDA(cudaMemcpy2DAsync(item_factors_out, size_t(h->k) * 8, h->F[1], size_t(h->kp) * 8, size_t(h->k) * 8,
+                                size_t(h->n[1]), cudaMemcpyDeviceToHost, h->stream));
+  }
+  double loss = 0.0;
+  rc = wals_finish_step(h, &loss);
+  if (rc) return rc;
+  if (err_user[1] != 0) return set_error(QMFB_ERR_NOT_SPD, "normal equations not positive definite (user half-step)");
+  // loss / nusers / nitems, WALSEngine.cpp:215
+  if (loss_out) *loss_out = loss / double(h->n[0]) / double(h->n[1]);
+  return QMFB_OK;
+}
+
+double* qmfb_wals_factors_device(qmfb_wals_t* h, int side) { return (h && side >= 0 && side <= 1) ? h->F[side] : nullptr; }
+void* qmfb_wals_stream(qmfb_wals_t* h) { return h ? h->stream : nullptr; }
+int64_t qmfb_wals_launch_count(qmfb_wals_t* h) { return h ? h->launches : 0; }
+int qmfb_wals_last_timing(qmfb_wals_t* h, float* gram_ms, float* solve_ms) {
+  if (!h) return set_error(QMFB_ERR_INVALID, "null handle");
+  if (gram_ms) *gram_ms = h->gram_ms;
+  if (solve_ms) *solve_ms = h->solve_ms;
+  return QMFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+"""Python drivers over the WALS part of the C ABI.
+
+``WalsEngineHandle`` wraps the host-buffer engine level (what the C++ ``qmf::WALSEngine`` binds);
+``csr_from_coo`` builds the CSR exactly as WALSEngine::groupSignals does
+(qmf/wals/WALSEngine.cpp:130-163): rows and entries in ascending raw-id order, duplicates kept.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import SIDE_ITEM, SIDE_USER, check, lib
+
+
+def csr_from_coo(row_id, col_id, val, col_ids_sorted=None):
+    """(row ids sorted unique, row_ptr int64, col_idx int32, val f64) with rows = ascending raw
+    row id, entries within a row ascending raw col id (stable for duplicates), col_idx = rank of
+    the raw col id among ``col_ids_sorted`` (default: the distinct col ids of the input)."""
+    row_id = np.asarray(row_id, dtype=np.int64)
+    col_id = np.asarray(col_id, dtype=np.int64)
+    val = np.asarray(val, dtype=np.float64)
+    perm = np.lexsort((col_id, row_id))
+    r, c, v = row_id[perm], col_id[perm], val[perm]
+    ids, counts = np.unique(r, return_counts=True)
+    row_ptr = np.zeros(len(ids) + 1, dtype=np.int64)
+    np.cumsum(counts, out=row_ptr[1:])
+    if col_ids_sorted is None:
+        col_ids_sorted = np.unique(col_id)
+    col_idx = np.searchsorted(col_ids_sorted, c).astype(np.int32)
+    return ids, row_ptr, col_idx, np.ascontiguousarray(v)
+
+
+class WalsEngineHandle:
+    """Engine-level handle: host buffers in, host buffers out (single GPU)."""
+
+    def __init__(self, nusers, nitems, nfactors, device=0):
+        self.nusers, self.nitems, self.k = int(nusers), int(nitems), int(nfactors)
+        h = C.c_void_p()
+        check(lib.qmfb_wals_create(device, self.nusers, self.nitems, self.k, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib.qmfb_wals_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _n(self, side):
+        return self.nusers if side == SIDE_USER else self.nitems
+
+    def set_csr(self, side, row_ptr, col_idx, val, row_begin=0):
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        if col_idx.size == 0:
+            col_idx, val = np.zeros(1, np.int32), np.zeros(1, np.float64)
+        check(lib.qmfb_wals_set_csr(self._h, side, row_begin, len(row_ptr) - 1, row_ptr, col_idx, val))
+
+    def set_factors(self, side, F):
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        assert F.shape == (self._n(side), self.k)
+        check(lib.qmfb_wals_set_factors(self._h, side, F))
+
+    def get_factors(self, side):
+        F = np.empty((self._n(side), self.k), dtype=np.float64)
+        check(lib.qmfb_wals_get_factors(self._h, side, F))
+        return F
+
+    def gram(self, side):
+        G = np.empty((self.k, self.k), dtype=np.float64)
+        check(lib.qmfb_wals_gram(self._h, side, G))
+        return G
+
+    def half_step(self, side, alpha, lam):
+        """returns the summed row losses divided by nusers*nitems (WALSEngine.cpp:215)"""
+        loss = C.c_double()
+        check(lib.qmfb_wals_half_step(self._h, side, alpha, lam, C.byref(loss)))
+        return loss.value / self.nusers / self.nitems
+
+    def epoch_host(self, alpha, lam, item_in=None, user_out=None, item_out=None):
+        loss = C.c_double()
+        pin = item_in.ctypes.data_as(C.c_void_p) if item_in is not None else None
+        pu = user_out.ctypes.data_as(C.c_void_p) if user_out is not None else None
+        pi = item_out.ctypes.data_as(C.c_void_p) if item_out is not None else None
+        check(lib.qmfb_wals_epoch_host(self._h, alpha, lam, pin, pu, pi, C.byref(loss)))
+        return loss.value
+
+    def launch_count(self):
+        return int(lib.qmfb_wals_launch_count(self._h))
+
+    def last_timing(self):
+        g, s = C.c_float(), C.c_float()
+        check(lib.qmfb_wals_last_timing(self._h, C.byref(g), C.byref(s)))
+        return g.value, s.value

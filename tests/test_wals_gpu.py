@@ -1,0 +1,139 @@
+"""GPU parity of the WALS half-step (Gram, per-row build + solve, loss) against the CPU oracle,
+through the C ABI.  Tolerances are the north_star's: 1e-9 relative on factors, 1e-12 relative on
+the objective."""
+import numpy as np
+import pytest
+
+from util import init_factors, rel_err, uniform_dataset
+
+pytestmark = pytest.mark.gpu
+
+FACTOR_TOL = 1e-9
+LOSS_TOL = 1e-12
+
+
+def _setup(nu, ni, nnz, k, seed, dup=0):
+    from qmf_b200 import WalsEngineHandle, csr_from_coo
+    u, i, v = uniform_dataset(nu, ni, nnz, seed, id_scale=(7, 3), dup=dup)
+    uids, urp, uci, uv = csr_from_coo(u, i, v)
+    iids, irp, ici, iv = csr_from_coo(i, u, v)
+    h = WalsEngineHandle(len(uids), len(iids), k)
+    h.set_csr(0, urp, uci, uv)
+    h.set_csr(1, irp, ici, iv)
+    return h, (urp, uci, uv), (irp, ici, iv), len(uids), len(iids)
+
+
+@pytest.mark.parametrize("n,k", [(1, 30), (17, 5), (1000, 30), (5000, 64), (3001, 100), (20000, 128), (40, 1)])
+def test_gram_matches_oracle(oracle_lib, n, k):
+    from qmf_b200 import WalsEngineHandle
+    Y = init_factors(n, k, seed=n + k, bound=0.5)
+    h = WalsEngineHandle(n, 1, k)
+    h.set_factors(0, Y)
+    G = h.gram(0)
+    Go = np.zeros((k, k))
+    oracle_lib.qmfo_gram(Y, n, k, Go)
+    assert rel_err(G, Go) < 1e-13
+    assert np.array_equal(G, G.T)
+
+
+@pytest.mark.parametrize("nu,ni,nnz,k,dup", [(300, 200, 6000, 30, 0), (200, 150, 4000, 64, 25), (400, 300, 12000, 128, 0),
+                                              (260, 210, 5000, 100, 0), (50, 40, 300, 8, 5)])
+def test_epochs_match_oracle(oracle_lib, nu, ni, nnz, k, dup):
+    h, ucsr, icsr, NU, NI = _setup(nu, ni, nnz, k, seed=11 * k, dup=dup)
+    Y0 = init_factors(NI, k, seed=5)
+    h.set_factors(1, Y0)
+    X = np.zeros((NU, k))
+    Y = Y0.copy()
+    alpha, lam = 40.0, 0.05
+    for epoch in range(3):
+        lu = h.half_step(0, alpha, lam)
+        li = h.half_step(1, alpha, lam)
+        lu_o = oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, ucsr[0], ucsr[1], ucsr[2], alpha, lam, NU, NI, 16)
+        li_o = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, icsr[0], icsr[1], icsr[2], alpha, lam, NU, NI, 16)
+        Xg, Yg = h.get_factors(0), h.get_factors(1)
+        assert rel_err(Xg, X) < FACTOR_TOL, (epoch, "user factors")
+        assert rel_err(Yg, Y) < FACTOR_TOL, (epoch, "item factors")
+        assert abs(lu - lu_o) <= LOSS_TOL * abs(lu_o), (epoch, lu, lu_o)
+        assert abs(li - li_o) <= LOSS_TOL * abs(li_o), (epoch, li, li_o)
+
+
+def test_rank_deficient_gram_backward_error(oracle_lib):
+    """Fewer rows than factors: G = Y^T Y is rank deficient, A = G + ... + lambda I has condition
+    number ~1e6, so the Cholesky (GPU) and Bunch-Kaufman (reference dsysv) solutions agree only to
+    cond * eps.  Parity bar here: forward error 1e-6 and a normal-equation residual no worse
+    than 4x the oracle's."""
+    h, ucsr, icsr, NU, NI = _setup(120, 90, 3000, 128, seed=1408)
+    k, alpha, lam = 128, 40.0, 0.05
+    Y0 = init_factors(NI, k, seed=5)
+    h.set_factors(1, Y0)
+    X = np.zeros((NU, k))
+    Y = Y0.copy()
+    h.half_step(0, alpha, lam)
+    oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, ucsr[0], ucsr[1], ucsr[2], alpha, lam, NU, NI, 16)
+    Xg = h.get_factors(0)
+    assert rel_err(Xg, X) < 1e-9
+    h.half_step(1, alpha, lam)
+    oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, icsr[0], icsr[1], icsr[2], alpha, lam, NU, NI, 16)
+    Yg = h.get_factors(1)
+    assert rel_err(Yg, Y) < 1e-6
+    G = X.T @ X
+    worst_g = worst_o = 0.0
+    for r in range(NI):
+        sl = slice(icsr[0][r], icsr[0][r + 1])
+        Ys, w = X[icsr[1][sl]], icsr[2][sl]
+        A = G + (Ys * (alpha * w)[:, None]).T @ Ys + lam * np.eye(k)
+        b = ((1 + alpha * w)[:, None] * Ys).sum(0)
+        worst_g = max(worst_g, np.abs(A @ Yg[r] - b).max() / np.abs(b).max())
+        worst_o = max(worst_o, np.abs(A @ Y[r] - b).max() / np.abs(b).max())
+    assert worst_g < max(4 * worst_o, 1e-12), (worst_g, worst_o)
+
+
+def test_row_shapes_edge_cases(oracle_lib):
+    """rows with 1 signal, exactly 16/17/32 signals (chunk boundaries), an empty row, a very long row"""
+    from qmf_b200 import WalsEngineHandle
+    k, ni = 30, 400
+    rng = np.random.default_rng(3)
+    lens = [1, 16, 17, 32, 0, 15, 33, 400, 2]
+    row_ptr = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=row_ptr[1:])
+    col = np.concatenate([np.sort(rng.choice(ni, n, replace=False)) for n in lens]).astype(np.int32)
+    val = rng.integers(1, 6, size=len(col)).astype(np.float64)
+    Y = init_factors(ni, k, seed=9, bound=0.3)
+    h = WalsEngineHandle(len(lens), ni, k)
+    h.set_csr(0, row_ptr, col, val)
+    h.set_factors(1, Y)
+    loss = h.half_step(0, 40.0, 0.05)
+    X = np.zeros((len(lens), k))
+    loss_o = oracle_lib.qmfo_wals_half_step(X, len(lens), Y, ni, k, row_ptr, col, val, 40.0, 0.05, len(lens), ni, 4)
+    assert rel_err(h.get_factors(0), X) < FACTOR_TOL
+    assert abs(loss - loss_o) <= LOSS_TOL * abs(loss_o)
+    assert np.all(h.get_factors(0)[4] == 0.0)  # empty row: A = G + lambda I, b = 0
+
+
+def test_not_spd_is_reported():
+    """lambda = 0 and fewer signals than factors with a zero Gram: singular system.  The reference
+    aborts (CHECK_EQ(result, 0), qmf/Matrix.cpp:94); the C ABI returns QMFB_ERR_NOT_SPD."""
+    from qmf_b200 import WalsEngineHandle, capi
+    k, ni = 30, 50
+    h = WalsEngineHandle(1, ni, k)
+    h.set_csr(0, np.array([0, 2], np.int64), np.array([1, 3], np.int32), np.array([1.0, 2.0]))
+    Y = np.zeros((ni, k))
+    Y[1, 0] = 1.0
+    Y[3, 1] = 1.0
+    h.set_factors(1, Y)
+    with pytest.raises(capi.QmfbError) as e:
+        h.half_step(0, 40.0, 0.0)
+    assert e.value.code == capi.ERR_NOT_SPD
+
+
+def test_epoch_host_roundtrip(oracle_lib):
+    h, ucsr, icsr, NU, NI = _setup(150, 100, 2500, 30, seed=77)
+    Y0 = init_factors(NI, 30, seed=6)
+    Xo, Yo = np.empty((NU, 30)), np.empty((NI, 30))
+    loss = h.epoch_host(40.0, 0.05, Y0, Xo, Yo)
+    X = np.zeros((NU, 30))
+    Y = Y0.copy()
+    oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, 30, ucsr[0], ucsr[1], ucsr[2], 40.0, 0.05, NU, NI, 16)
+    lo = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, 30, icsr[0], icsr[1], icsr[2], 40.0, 0.05, NU, NI, 16)
+    assert rel_err(Xo, X) < FACTOR_TOL and rel_err(Yo, Y) < FACTOR_TOL
+    assert abs(loss - lo) <= LOSS_TOL * abs(lo)
