@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — WALS epoch throughput (BASELINE.json metric: "WALS s/epoch & nnz/s at 1/2/4/8 B200")
+on the Netflix-shaped synthetic config C4 (480k users x 17.8k items, 100M nnz, k=128, FP64).
+
+  python bench.py --gpus 1 --steps K --warmup W                 # our arm, one GPU
+  torchrun ... bench.py --gpus N --steps K --warmup W           # our arm, N ranks (row-partitioned)
+  python bench.py --impl reference --steps K --warmup W         # the reference's CPU path on host cores
+
+A step = one WALS epoch (user half-step + item half-step: Gram, per-row build, solve, loss).
+`value` = nnz per epoch / device seconds per epoch (each nnz is touched twice per epoch), inputs
+resident in HBM.  `e2e` = the same through host buffers (H2D of the item factors, D2H of both
+factor matrices and the loss every step).  The dataset (CSR+CSC 2.4 GB, factors 0.5 GB) is far
+larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALPHA, LAMBDA = 40.0, 0.05          # reference defaults (qmf/wals.cpp:28-29)
+FP64_PEAK_TFLOPS = 37.1             # measured: profiles/r01_fp64_peak.txt (DMMA.8x8x4 register loop)
+
+
+def algorithmic_flops(n_rows, nnz, k):
+    """SURVEY.md §8(d), symmetric-aware, one half-step over n_rows rows with nnz signals."""
+    build = nnz * (k * (k + 1) + 2 * k)
+    solve = n_rows * (k ** 3 / 3.0 + 2 * k * k)
+    loss = n_rows * (2 * k * k + 3 * k)
+    return build + solve + loss
+
+
+def algorithmic_bytes(n_rows, n_other, nnz, k):
+    """CSR idx32+val64, one gathered row of k doubles per nnz, factor write, Gram read of the other side"""
+    return nnz * 12 + nnz * 8 * k + n_rows * 8 * k + n_other * 8 * k
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # median over samples taken under load (top half)
+            load = sorted(sm)[len(sm) // 2:]
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / CPU baseline leg (the only place bench.py executes anything under oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_problem(cfg, su, si, sg, seed=123):
+    from qmf_b200.datagen import uniform_row_sample
+    nu, ni, nnz, k = cfg
+    p = nnz / (nu * ni)
+    rng = np.random.default_rng(seed)
+    user_rows = uniform_row_sample(nu, ni, p, su, seed + 1)
+    item_rows = uniform_row_sample(ni, nu, p, si, seed + 2)
+    Yi = rng.uniform(-0.01, 0.01, size=(ni, k))     # item factors (fixed side of the user step)
+    Yu = rng.uniform(-0.3, 0.3, size=(nu, k))       # user factors (fixed side of the item step)
+    return dict(user_rows=user_rows, item_rows=item_rows, Yi=Yi, Yu=Yu, sg=sg)
+
+
+def cpu_sample_step(cfg, prob, threads):
+    """One bounded sample of the reference's epoch: `su` user rows + `si` item rows through the
+    reference's own updateFactorsForOne on its ParallelExecutor (oracle/_ref), plus its serial
+    Gram on `sg` rows; extrapolated to the full epoch by row counts.  Returns (epoch_seconds
+    estimate, sample_seconds, kind)."""
+    import oracle
+    nu, ni, nnz, k = cfg
+    if oracle.ref_available():
+        L = oracle.ref()
+        L.ref_set_min_log_level(2)
+        sec = C.c_double()
+        t_meas = 0.0
+        est = 0.0
+        for rows, Y, nright, nleft_total in ((prob["user_rows"], prob["Yi"], ni, nu), (prob["item_rows"], prob["Yu"], nu, ni)):
+            rp, col, val = rows
+            ns = len(rp) - 1
+            # Gram of the fixed side: the reference's (serial under OMP_NUM_THREADS=1) computeXtX
+            sg = min(prob["sg"], nright)
+            G = np.zeros((k, k))
+            t0 = time.perf_counter()
+            L.ref_gram(np.ascontiguousarray(Y[:sg]), sg, k, threads, 1, G)
+            tg = time.perf_counter() - t0
+            X = np.zeros((ns, k))
+            L.ref_wals_update_rows(X, ns, Y, nright, k, rp, col, val, G, ALPHA, LAMBDA, threads, C.byref(sec))
+            t_meas += tg + sec.value
+            est += tg * (nright / sg) + sec.value * (nleft_total / ns)
+        return est, t_meas, "reference"
+    # oracle port (single thread): smaller sample
+    L = oracle.oracle()
+    t_meas = est = 0.0
+    for rows, Y, nright, nleft_total in ((prob["user_rows"], prob["Yi"], ni, nu), (prob["item_rows"], prob["Yu"], nu, ni)):
+        rp, col, val = rows
+        ns = max(1, (len(rp) - 1) // 16)
+        G = np.zeros((k, k))
+        sg = min(prob["sg"] // 4, nright)
+        t0 = time.perf_counter()
+        L.qmfo_gram(np.ascontiguousarray(Y[:sg]), sg, k, G)
+        tg = time.perf_counter() - t0
+        x = np.zeros(k)
+        t0 = time.perf_counter()
+        for r in range(ns):
+            L.qmfo_wals_update_row(Y, k, col[rp[r]:rp[r + 1]], val[rp[r]:rp[r + 1]], rp[r + 1] - rp[r], G, ALPHA, LAMBDA, x)
+        tr = time.perf_counter() - t0
+        t_meas += tg + tr
+        est += tg * (nright / sg) + tr * (nleft_total / ns)
+    return est, t_meas, "port"
+
+
+def sample_sizes(cfg):
+    nu, ni, nnz, k = cfg
+    # ~2.5 M nnz per side at k=128 (~1.7 s per side on 16 threads), scaled by k^2 for smaller k
+    budget = 2.5e6 * (128.0 / k) ** 2
+    su = int(min(nu, max(64, budget / (nnz / nu))))
+    si = int(min(ni, max(16, budget / (nnz / ni))))
+    return su, si, 8000
+
+
+def run_reference(args, cfg, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", "1")       # the reference's OpenMP Gram is racy
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    nu, ni, nnz, k = cfg
+    threads = os.cpu_count() or 1
+    su, si, sg = sample_sizes(cfg)
+    prob = cpu_sample_problem(cfg, su, si, sg)
+    for _ in range(args.warmup):
+        cpu_sample_step(cfg, prob, threads)
+    ests, meas, kind = [], [], "reference"
+    for _ in range(args.steps):
+        e, m, kind = cpu_sample_step(cfg, prob, threads)
+        ests.append(e)
+        meas.append(m)
+    epoch_s = float(np.mean(ests))
+    value = nnz / epoch_s
+    sample = ("%d of %d user rows + %d of %d item rows of the %s uniform problem through the reference's "
+              "updateFactorsForOne on %d pool threads (+ its serial Gram on %d rows), extrapolated to one epoch by row "
+              "count; OMP_NUM_THREADS=1" % (su, nu, si, ni, workload, threads, sg))
+    line = {
+        "impl": "reference", "metric": "wals_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(meas)) * 1e3,
+        "est_epoch_s": epoch_s, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload, "nusers": nu, "nitems": ni, "nnz": nnz, "nfactors": k,
+                                        "alpha": ALPHA, "lambda": LAMBDA},
+        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": threads if kind == "reference" else 1, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, cfg, workload):
+    import torch
+    import torch.distributed as dist
+    from qmf_b200 import capi
+    from qmf_b200.datagen import init_item_factors, uniform_csr_torch
+    from qmf_b200.wals_dist import ShardedWals
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    nu, ni, nnz, k = cfg
+
+    csr_user, csr_item = uniform_csr_torch(nu, ni, nnz, seed=20240501, device=device)
+    sw = ShardedWals(nu, ni, k, csr_user, csr_item, device, rank, world)
+    Y0 = init_item_factors(ni, k, seed=7)
+    sw.set_factors(1, Y0)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sw.epoch(ALPHA, LAMBDA)
+    barrier()
+    sw.check_error()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[{n: torch.cuda.Event(enable_timing=True) for n in ("gram0", "solve0", "solve1")} for _ in range(2)]
+          for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sw.launches
+    barrier()
+    t0.record()
+    loss = None
+    for s in range(args.steps):
+        loss = sw.epoch(ALPHA, LAMBDA, ev[s])
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    value = nnz / (ms_per_step * 1e-3)
+    launches = sw.launches - launches0
+    loss_value = float(loss.item())
+    sw.check_error()
+
+    # dominant kernel: wals_solve_kernel (2 launches per epoch) on this rank's shards
+    solve_ms = [[e[h]["solve0"].elapsed_time(e[h]["solve1"]) for h in range(2)] for e in ev]
+    gram_ms = [[e[h]["gram0"].elapsed_time(e[h]["solve0"]) for h in range(2)] for e in ev]
+    fl = by = 0.0
+    for side in (0, 1):
+        sh = sw.shard[side]
+        fl += algorithmic_flops(sh["end"] - sh["begin"], sh["nnz"], k)
+        by += algorithmic_bytes(sh["end"] - sh["begin"], sw.n[1 - side], sh["nnz"], k)
+    solve_s_per_epoch = float(np.mean([sum(x) for x in solve_ms])) * 1e-3
+    achieved_tf = fl / solve_s_per_epoch * 1e-12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {
+        "kernel": "wals_solve_kernel<16> (2 launches/epoch: user rows, item rows)",
+        "bound": "tensor", "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+        "frac": achieved_tf / FP64_PEAK_TFLOPS, "traffic": None,
+        "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json "
+                       "has no FP64 entry (its bf16 figure does not apply to an FP64 kernel)",
+        "algorithmic_flops_per_epoch": fl, "solve_ms_user_item": [float(np.mean([x[0] for x in solve_ms])),
+                                                                  float(np.mean([x[1] for x in solve_ms]))],
+        "gram_ms_user_item": [float(np.mean([x[0] for x in gram_ms])), float(np.mean([x[1] for x in gram_ms]))],
+        "hbm": {"achieved": by / solve_s_per_epoch * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": by / solve_s_per_epoch * 1e-9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+    }
+
+    # ---- e2e: host buffers in/out every step --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        item_in = torch.from_numpy(Y0).pin_memory()
+        ub, ue = sw.shard[0]["begin"], sw.shard[0]["end"]
+        ib, ie = sw.shard[1]["begin"], sw.shard[1]["end"]
+        user_out = torch.empty((ue - ub, k), dtype=torch.float64).pin_memory()
+        item_out = torch.empty((ie - ib, k), dtype=torch.float64).pin_memory()
+        loss_host = torch.empty(1, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            sw.F[1][:, :k].copy_(item_in, non_blocking=True)
+            l = sw.epoch(ALPHA, LAMBDA)
+            user_out.copy_(sw.F[0][ub:ue, :k], non_blocking=True)
+            item_out.copy_(sw.F[1][ib:ie, :k], non_blocking=True)
+            loss_host.copy_(l, non_blocking=True)
+
+        if world == 1:
+            # through the engine-level C ABI (qmfb_wals_epoch_host), the call qmf::WALSEngine binds
+            from qmf_b200 import WalsEngineHandle
+            h = WalsEngineHandle(nu, ni, k, device=local_rank)
+            for side, (rp, col, val) in enumerate((csr_user, csr_item)):
+                h.set_csr(side, rp.cpu().numpy(), col.cpu().numpy(), val.cpu().numpy())
+            uo = torch.empty((nu, k), dtype=torch.float64).pin_memory()
+            io = torch.empty((ni, k), dtype=torch.float64).pin_memory()
+            h.epoch_host(ALPHA, LAMBDA, item_in.numpy(), uo.numpy(), io.numpy())
+            torch.cuda.synchronize()
+            tt = time.perf_counter()
+            for _ in range(args.steps):
+                l2 = h.epoch_host(ALPHA, LAMBDA, item_in.numpy(), uo.numpy(), io.numpy())
+            e2e_ms = (time.perf_counter() - tt) * 1e3 / args.steps
+            h2d, d2h = ni * k * 8, (nu + ni) * k * 8 + 8 + 16
+            launches_e2e = h.launch_count()
+            h.close()
+            e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "nnz/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e2e_ms, "api": "qmfb_wals_epoch_host (C ABI, pinned host buffers, wall clock around the "
+                   "synchronous call)", "loss": l2, "launches": launches_e2e}
+        else:
+            e2e_step()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                e2e_step()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item()) / args.steps
+            e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "nnz/s", "h2d_bytes_per_step": world * ni * k * 8,
+                   "d2h_bytes_per_step": (nu + ni) * k * 8 + 8 * world, "ms_per_step": e2e_ms,
+                   "api": "ShardedWals.epoch with pinned host factors in/out on every rank (CUDA events, max over ranks)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        su, si, sg = sample_sizes(cfg)
+        prob = cpu_sample_problem(cfg, su, si, sg)
+        est, meas, kind = cpu_sample_step(cfg, prob, threads)
+        cpu_baseline = {"value": nnz / est, "unit": "nnz/s", "cores": threads if kind == "reference" else 1, "kind": kind,
+                        "est_epoch_s": est, "sample_s": meas,
+                        "sample": "%d of %d user rows + %d of %d item rows (+ serial Gram on %d rows) through the "
+                                  "reference's updateFactorsForOne, extrapolated by row count" % (su, nu, si, ni, sg)}
+
+    if rank == 0:
+        line = {
+            "metric": "wals_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "s_per_epoch": ms_per_step * 1e-3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "nusers": nu, "nitems": ni, "nnz": nnz, "nfactors": k, "alpha": ALPHA,
+                       "lambda": LAMBDA, "parallelism": "rows x%d" % world,
+                       "l2": "inputs (2.9 GB) larger than the 126 MB L2; no flush"},
+            "loss": loss_value, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
+            "cpu_baseline": cpu_baseline, "lib": os.path.relpath(capi.LIB_PATH, ROOT),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c3", "c4"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    from qmf_b200.datagen import CONFIGS
+    cfg = CONFIGS[args.workload]
+    names = {"c1": "C1 uniform 10k x 5k, 500k nnz, k=30", "c3": "C3 MovieLens-20M-shaped 138k x 27k, 20M nnz, k=64",
+             "c4": "C4 Netflix-shaped 480k x 17.8k, 100M nnz, k=128"}
+    if args.impl == "reference":
+        run_reference(args, cfg, names[args.workload])
+    else:
+        run_ours(args, cfg, names[args.workload])
+
+
+if __name__ == "__main__":
+    main()

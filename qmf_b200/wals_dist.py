@@ -1,0 +1,154 @@
+"""One-process-per-GPU WALS driver over the kernel-level C ABI (qmfb_gram_dev / qmfb_wals_solve_dev).
+
+Sharding: users and items are each split into `world` contiguous row ranges
+balanced by nnz.  Every rank keeps full replicas of both factor matrices plus the CSR rows of
+its user range and the CSC rows of its item range.  One half-step "update side S" is
+
+  1. partial Gram over THIS rank's rows of the other side   (qmfb_gram_dev)
+  2. allreduce(sum) of the packed Gram (<= 68 KB)            (NCCL)
+  3. solve this rank's rows of S                             (qmfb_wals_solve_dev)
+  4. broadcast each rank's freshly solved rows to all        (NCCL, unequal shards allowed)
+  5. allreduce(sum) of the loss scalar                       (NCCL)
+
+torch is used for device memory, streams and torch.distributed only.  With world == 1 no
+collective is issued.  The same class runs on CPU tensors with the `gloo` backend when a
+`kernels` object is injected (tests/test_wals_dist_cpu.py exercises the sharding/exchange logic
+that way); the product path always uses the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+try:
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    dist = None
+
+
+def balanced_row_ranges(row_ptr, world):
+    """Split rows into `world` contiguous ranges with ~equal nnz (prefix sum over row_ptr).
+    Returns a list of (begin, end)."""
+    rp = row_ptr.detach().cpu().numpy() if isinstance(row_ptr, torch.Tensor) else np.asarray(row_ptr)
+    nrows = len(rp) - 1
+    nnz = int(rp[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = nnz * r // world
+        c = int(np.searchsorted(rp, target, side="left"))
+        c = min(max(c, cuts[-1]), nrows)
+        cuts.append(c)
+    cuts.append(nrows)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class CudaKernels:
+    """The product path: hand-written sm_100a kernels behind the C ABI."""
+
+    def __init__(self):
+        from . import capi
+        self.capi = capi
+        self.lib = capi.lib
+
+    def padded_k(self, k):
+        return self.capi.check(self.lib.qmfb_padded_k(k))
+
+    def gram_packed_len(self, k):
+        return int(self.lib.qmfb_gram_packed_len(k))
+
+    def gram_workspace_len(self, k):
+        return int(self.lib.qmfb_gram_workspace_len(k))
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def gram(self, Y, row_begin, row_end, k, ws, out):
+        self.capi.check(self.lib.qmfb_gram_dev(self._stream(), Y.data_ptr(), Y.stride(0), row_begin, row_end, k,
+                                               ws.data_ptr(), out.data_ptr()))
+
+    def solve(self, X, row_offset, Y, k, row_ptr, col, val, order, gram, alpha, lam, row_loss, loss_sum, scratch):
+        self.capi.check(self.lib.qmfb_wals_solve_dev(
+            self._stream(), X.data_ptr(), X.stride(0), row_offset, Y.data_ptr(), Y.stride(0), k, row_ptr.data_ptr(),
+            col.data_ptr(), val.data_ptr(), order.data_ptr(), order.numel(), gram.data_ptr(), alpha, lam,
+            row_loss.data_ptr(), loss_sum.data_ptr(), scratch.data_ptr()))
+
+    launches_per_half_step = 4  # gram_partial, gram_reduce, wals_solve, sum
+
+
+class ShardedWals:
+    """State of one rank.  `csr[side]` = (row_ptr int64 [n+1], col int32 [nnz], val f64 [nnz]) of
+    the FULL problem for that orientation, on `device`; the rank keeps only its slice."""
+
+    def __init__(self, nusers, nitems, k, csr_user, csr_item, device, rank=0, world=1, kernels=None):
+        self.n = (int(nusers), int(nitems))
+        self.k = int(k)
+        self.rank, self.world = rank, world
+        self.device = device
+        self.kern = kernels if kernels is not None else CudaKernels()
+        self.kp = self.kern.padded_k(self.k)
+        self.F = [torch.zeros(self.n[s], self.kp, dtype=torch.float64, device=device) for s in (0, 1)]
+        self.ranges, self.shard = [], []
+        for side, (rp, col, val) in enumerate((csr_user, csr_item)):
+            ranges = balanced_row_ranges(rp, world)
+            b, e = ranges[rank]
+            p0, p1 = int(rp[b]), int(rp[e])
+            lrp = (rp[b:e + 1] - rp[b]).contiguous()
+            lcol = col[p0:p1].contiguous() if p1 > p0 else torch.zeros(1, dtype=torch.int32, device=device)
+            lval = val[p0:p1].contiguous() if p1 > p0 else torch.zeros(1, dtype=torch.float64, device=device)
+            lens = lrp[1:] - lrp[:-1]
+            order = torch.argsort(lens, descending=True, stable=True).to(torch.int32).contiguous()
+            self.ranges.append(ranges)
+            self.shard.append(dict(begin=b, end=e, row_ptr=lrp, col=lcol, val=lval, order=order, nnz=p1 - p0))
+        self.gram_packed = torch.zeros(self.kern.gram_packed_len(self.k), dtype=torch.float64, device=device)
+        self.gram_ws = torch.empty(self.kern.gram_workspace_len(self.k), dtype=torch.float64, device=device)
+        self.row_loss = torch.zeros(max(max(s["end"] - s["begin"] for s in self.shard), 1), dtype=torch.float64,
+                                    device=device)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
+        self.scratch = torch.zeros(2, dtype=torch.int32, device=device)
+        self.launches = 0
+        self.timing = None  # optional dict of torch.cuda.Event pairs filled by half_step(record=True)
+
+    def set_factors(self, side, F):
+        """F: [n, k] tensor/ndarray (host or device)"""
+        F = torch.as_tensor(F, dtype=torch.float64)
+        self.F[side][:, :self.k].copy_(F, non_blocking=True)
+
+    def get_factors(self, side):
+        return self.F[side][:, :self.k]
+
+    def half_step(self, side, alpha, lam, events=None):
+        """Returns the device scalar holding the summed loss of ALL rows of `side` (all ranks)."""
+        other = 1 - side
+        sh, osh = self.shard[side], self.shard[other]
+        if events is not None:
+            events["gram0"].record()
+        self.kern.gram(self.F[other], osh["begin"], osh["end"], self.k, self.gram_ws, self.gram_packed)
+        if self.world > 1:
+            dist.all_reduce(self.gram_packed)
+        if events is not None:
+            events["solve0"].record()
+        # leftData.setFactors(0) (WALSEngine.cpp:170-171) — rows of this shard; the others arrive in step 4
+        self.F[side][sh["begin"]:sh["end"]].zero_()
+        self.kern.solve(self.F[side], sh["begin"], self.F[other], self.k, sh["row_ptr"], sh["col"], sh["val"],
+                        sh["order"], self.gram_packed, alpha, lam, self.row_loss, self.loss_sum, self.scratch)
+        if events is not None:
+            events["solve1"].record()
+        self.launches += self.kern.launches_per_half_step
+        if self.world > 1:
+            for r, (b, e) in enumerate(self.ranges[side]):
+                if e > b:
+                    dist.broadcast(self.F[side][b:e], src=r)
+            dist.all_reduce(self.loss_sum)
+        return self.loss_sum
+
+    def epoch(self, alpha, lam, events=None):
+        """user half-step, then item half-step; returns the item-step loss / nusers / nitems as a
+        device tensor (WALSEngine::optimize, WALSEngine.cpp:86-92)"""
+        self.half_step(0, alpha, lam, events[0] if events else None)
+        loss = self.half_step(1, alpha, lam, events[1] if events else None)
+        return loss / self.n[0] / self.n[1]
+
+    def check_error(self):
+        if int(self.scratch[1].item()) != 0:
+            raise RuntimeError("normal equations not positive definite (reference: dsysv failed, qmf/Matrix.cpp:94)")
