@@ -118,7 +118,7 @@ int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset
     return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_dev: bad argument");
   }
   SolveParams prm{X, ldx, row_offset, Y, ldy, k, row_ptr, col, val, order, int(nrows), gram_packed, alpha, lambda,
-                  row_loss, scratch, scratch + 1};
+                  row_loss, scratch + 1};
   auto st = static_cast<cudaStream_t>(stream);
   switch (kp / 8) {
     case 4: return launch_solve<4>(st, prm, loss_sum, scratch);

@@ -10,22 +10,33 @@
 //    shared-memory-fed loop below reaches ~35 TFLOP/s in isolation.
 //  * A row's k x k system is held as the upper triangle of 8x8 tiles.  Warp w of a CTA owns
 //    tile-rows w and NT-1-w (NT+1 tiles -> perfectly balanced), accumulators live in registers.
-//  * Gathered factor rows are staged into padded shared memory (row stride KP+8 doubles ->
-//    conflict-free DMMA fragment loads) by the TMA engine: one cp.async.bulk per gathered row,
-//    completion on an mbarrier, NSTAGE-deep ring, no register staging.
-//  * After the build the tiles are written to shared memory (aliasing the staging ring), the
-//    Gram matrix and lambda are added, and a blocked right-looking Cholesky (8-wide panels,
-//    DMMA trailing updates, b carried as an extra tile column so the forward solve is free)
-//    followed by a single-warp blocked back substitution produces x.  A never leaves the SM.
-//  * Rows are scheduled longest-first through an atomic counter (persistent CTAs).
+//  * Factor rows are staged into padded shared memory (row stride KP+8 doubles -> conflict-free
+//    DMMA fragment loads) through an mbarrier-tracked ring, no register staging.  Gathered rows
+//    (solve kernel) use 16-byte cp.async (LDGSTS) issued by all threads: the TMA engine's
+//    outstanding-request window caps a DRAM-resident 1 KB-row gather at ~5 B/clk/SM
+//    (profiles/r01_solve_v1_*: 49 % of warp samples waiting on the full barrier), LDGSTS has no
+//    such cap.  The Gram kernel streams contiguous rows with TMA bulk copies (cp.async.bulk).
+//  * Accumulators start from the Gram tiles; after the build lambda is added and the tiles go to
+//    shared memory, where a blocked right-looking Cholesky (8-wide panels, DMMA trailing
+//    updates, look-ahead on the diagonal tile, b carried as an extra tile column so the forward
+//    solve is free) and a blocked back substitution produce x.  A never leaves the SM.
+//  * One persistent CTA per SM at k=128: build (DMMA-bound) and solve (latency-bound) phases
+//    alternate instead of overlapping, because FP64 scalar ops of a solving CTA starve behind a
+//    co-resident CTA's DMMAs on the shared FP64 pipe (profiles/r01_solve_v1/v2).  The staging
+//    ring is separate from the tile storage, so the next row's first chunks are already in
+//    flight while the current row is being solved.
+//  * Rows are sorted longest-first and dealt to the CTAs in serpentine order (static schedule,
+//    so the next row is known early enough to prefetch).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace qmfb {
 
 constexpr int kChunk = 16;   // gathered rows per pipeline stage
-constexpr int kStages = 4;   // ring depth
+constexpr int kStages = 7;   // ring depth (chunks in flight, may span two consecutive rows)
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers
@@ -65,6 +76,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// 16-byte asynchronous copy global -> shared (SASS: LDGSTS), L1 bypass
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (count pre-charged at init)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // D(8x8) += A(8x4) * B(4x8), FP64.  Lane T holds A[T/4][T%4], B[T%4][T/4], C[T/4][2*(T%4)+{0,1}].
@@ -91,20 +110,22 @@ struct WalsSmem {
   static constexpr int LD = KP + 8;            // staging row stride (doubles); LD % 16 == 8
   static constexpr int NWARPS = NT / 2;
   static constexpr int NTHREADS = NWARPS * 32;  // == 2 * KP
+  static constexpr int NACC = NT + 1;           // tiles per warp (rows w and NT-1-w)
   static constexpr int NTILE_A = NT * (NT + 1) / 2;
   static constexpr int NTILE = NTILE_A + NT;    // + one tile column for b
   static constexpr size_t kStageBytes = size_t(kStages) * kChunk * LD * 8;
   static constexpr size_t kTileBytes = size_t(NTILE) * 64 * 8;
-  static constexpr size_t kMainBytes = kStageBytes > kTileBytes ? kStageBytes : kTileBytes;
-  static constexpr size_t kOffWts = kMainBytes;                              // kStages*2*kChunk doubles
+  static constexpr size_t kOffStage = 0;
+  static constexpr size_t kOffTiles = kStageBytes;
+  static constexpr size_t kOffWts = kOffTiles + kTileBytes;                  // kStages*2*kChunk doubles
   static constexpr size_t kOffW = kOffWts + size_t(kStages) * 2 * kChunk * 8;  // NT inverse diagonal tiles
   static constexpr size_t kOffB = kOffW + size_t(NT) * 64 * 8;               // b copy (KP)
   static constexpr size_t kOffX = kOffB + size_t(KP) * 8;                    // x (KP)
-  static constexpr size_t kOffR = kOffX + size_t(KP) * 8;                    // back-substitution rhs (KP)
-  static constexpr size_t kOffBh = kOffR + size_t(KP) * 8;                   // b half sums (2*KP)
+  static constexpr size_t kOffR = kOffX + size_t(KP) * 8;                    // back-substitution rhs (8)
+  static constexpr size_t kOffBh = kOffR + 64;                               // b half sums (2*KP)
   static constexpr size_t kOffBar = kOffBh + size_t(KP) * 16;                // full[kStages], empty[kStages]
-  static constexpr size_t kOffMisc = kOffBar + size_t(kStages) * 16;
-  static constexpr size_t kBytes = kOffMisc + 64;
+  static constexpr size_t kOffMap = kOffBar + size_t(kStages) * 16;          // (J1,J2) of every tile, 2 bytes each
+  static constexpr size_t kBytes = kOffMap + ((size_t(NTILE) * 2 + 15) / 16) * 16;
 
   // tile (I,J), I <= J <= NT (J == NT is the b column), row-major upper storage
   __host__ __device__ static constexpr int tidx(int I, int J) { return I * (NT + 1) - I * (I - 1) / 2 + (J - I); }
@@ -112,167 +133,71 @@ struct WalsSmem {
   __host__ __device__ static constexpr int gidx(int I, int J) { return I * NT - I * (I - 1) / 2 + (J - I); }
 };
 
-struct RowSource {
-  const double* Y;       // right-side factors, row stride ldy (>= KP, zero padded)
-  int64_t ldy;
-  const int32_t* col;    // gather indices (nullptr => contiguous rows p0..p1 of Y, Gram mode)
-  const double* val;
-  double alpha;
-};
-
 // ------------------------------------------------------------------------------------------
-// build: accumulate sum_s wa[s] * y_s y_s^T (upper tiles) and, in gather mode, b = sum_s wb[s] y_s
+// DMMA inner loop of one staged chunk for warp role W: tile rows I0 = W (NT-W tiles) and
+// I1 = NT-1-W (W+1 tiles); acc[0..N0) are row I0, acc[N0..NT+1) row I1.  This is the only code
+// that differs between warps; everything else in the kernels is a single copy.
 // ------------------------------------------------------------------------------------------
-template <int NT, bool GATHER>
-struct Producer {
-  using SM = WalsSmem<NT>;
-  const double* src;  // next chunk's gathered row for this lane
-  double wa, wb;
-  double csum;
-
-  __device__ __forceinline__ void load(const RowSource& rs, int64_t p0, int64_t p1, int n, int lane) {
-    const int64_t p = p0 + int64_t(n) * kChunk + lane;
-    const bool valid = lane < kChunk && p < p1;
-    if (GATHER) {
-      const int32_t c = valid ? __ldg(rs.col + p) : 0;
-      const double v = valid ? __ldg(rs.val + p) : 0.0;
-      src = rs.Y + int64_t(c) * rs.ldy;
-      wa = valid ? rs.alpha * v : 0.0;          // WALSEngine.cpp:282  alpha * r
-      wb = valid ? 1.0 + rs.alpha * v : 0.0;    // WALSEngine.cpp:280  1 + alpha * r
-    } else {
-      src = rs.Y + (valid ? p : 0) * rs.ldy;
-      wa = valid ? 1.0 : 0.0;
-      wb = 0.0;
-    }
-  }
-
-  // issue chunk n of the current row (global chunk number gn) and prefetch chunk n+1's indices
-  __device__ __forceinline__ void issue(unsigned char* smem, const RowSource& rs, int64_t p0, int64_t p1, int n,
-                                        uint32_t gn, int lane) {
-    double* stagebuf = reinterpret_cast<double*>(smem);
-    double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
-    uint64_t* empty = full + kStages;
-    const uint32_t st = gn % kStages;
-    if (gn >= kStages) mbar_wait(&empty[st], ((gn / kStages) & 1u) ^ 1u);
-    if (lane < kChunk) {
-      wts[st * 2 * kChunk + lane] = wa;
-      wts[st * 2 * kChunk + kChunk + lane] = wb;
-    }
-    csum += wb;
-    __syncwarp();
-    if (lane == 0) mbar_arrive_expect_tx(&full[st], uint32_t(kChunk) * SM::KP * 8);
-    __syncwarp();
-    if (lane < kChunk) bulk_g2s(stagebuf + (size_t(st) * kChunk + lane) * SM::LD, src, SM::KP * 8, &full[st]);
-    load(rs, p0, p1, n + 1, lane);
-  }
-};
-
-template <int NT, int W, bool GATHER, typename Epilogue>
-__device__ __forceinline__ void build_warp(unsigned char* smem, const RowSource& rs, int64_t p0, int64_t p1,
-                                           uint32_t chunk_base, double& csum_out, Epilogue&& epilogue) {
+template <int NT, int W>
+__device__ __forceinline__ void chunk_mma(double (&acc)[NT + 1][2], const double* sb, const double* wt, int lane) {
   using SM = WalsSmem<NT>;
   constexpr int I0 = W, I1 = NT - 1 - W, N0 = NT - I0, N1 = NT - I1, D = I1 - I0;
-  const int lane = threadIdx.x & 31;
-  const double* stagebuf = reinterpret_cast<const double*>(smem);
-  const double* wts = reinterpret_cast<const double*>(smem + SM::kOffWts);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
-  uint64_t* empty = full + kStages;
-
-  double acc0[N0][2], acc1[N1][2];
 #pragma unroll
-  for (int j = 0; j < N0; ++j) acc0[j][0] = acc0[j][1] = 0.0;
+  for (int s0 = 0; s0 < kChunk; s0 += 4) {
+    const double* p = sb + (s0 + (lane & 3)) * SM::LD + (lane >> 2) + 8 * I0;
+    const double wa = wt[s0 + (lane & 3)];
+    double bf[N0];
 #pragma unroll
-  for (int j = 0; j < N1; ++j) acc1[j][0] = acc1[j][1] = 0.0;
-  double bacc = 0.0;
-  const int bi = threadIdx.x % SM::KP, bh = threadIdx.x / SM::KP;
-
-  const int nch = int((p1 - p0 + kChunk - 1) / kChunk);
-  Producer<NT, GATHER> prod;
-  prod.csum = 0.0;
-  if (W == 0) {
-    prod.load(rs, p0, p1, 0, lane);
-    const int pre = nch < kStages - 1 ? nch : kStages - 1;
-    for (int n = 0; n < pre; ++n) prod.issue(smem, rs, p0, p1, n, chunk_base + n, lane);
+    for (int j = 0; j < N0; ++j) bf[j] = p[8 * j];
+    const double a0 = bf[0] * wa;
+    const double a1 = bf[D] * wa;
+#pragma unroll
+    for (int j = 0; j < N0; ++j) dmma(acc[j], a0, bf[j]);
+#pragma unroll
+    for (int j = 0; j < N1; ++j) dmma(acc[N0 + j], a1, bf[D + j]);
   }
-  for (int c = 0; c < nch; ++c) {
-    const uint32_t gc = chunk_base + c;
-    const uint32_t st = gc % kStages;
-    if (W == 0) {
-      const int n = c + kStages - 1;
-      if (n < nch) prod.issue(smem, rs, p0, p1, n, chunk_base + n, lane);
-    }
-    mbar_wait(&full[st], (gc / kStages) & 1u);
-    const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
-    const double* wt = wts + st * 2 * kChunk;
-#pragma unroll
-    for (int s0 = 0; s0 < kChunk; s0 += 4) {
-      const double* p = sb + (s0 + (lane & 3)) * SM::LD + (lane >> 2) + 8 * I0;
-      const double wa = wt[s0 + (lane & 3)];
-      double bf[N0];
-#pragma unroll
-      for (int j = 0; j < N0; ++j) bf[j] = p[8 * j];
-      const double a0 = bf[0] * wa;
-      const double a1 = bf[D] * wa;
-#pragma unroll
-      for (int j = 0; j < N0; ++j) dmma(acc0[j], a0, bf[j]);
-#pragma unroll
-      for (int j = 0; j < N1; ++j) dmma(acc1[j], a1, bf[D + j]);
-    }
-    if (GATHER) {
-#pragma unroll
-      for (int s = 0; s < kChunk / 2; ++s) bacc += wt[kChunk + 2 * s + bh] * sb[(2 * s + bh) * SM::LD + bi];
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
-  }
-  if (W == 0) csum_out = prod.csum;
-  epilogue(acc0, acc1, bacc);
 }
 
-// ------------------------------------------------------------------------------------------
-// Gram kernel: partial upper-tile Gram of rows [r0, r1) per CTA, then a deterministic reduce
-// ------------------------------------------------------------------------------------------
 template <int NT, int W>
-struct GramEpilogue {
-  double* out;  // this CTA's packed partial (NTILE_A * 64 doubles)
-  template <int N0, int N1>
-  __device__ __forceinline__ void operator()(double (&acc0)[N0][2], double (&acc1)[N1][2], double) const {
-    using SM = WalsSmem<NT>;
-    const int lane = threadIdx.x & 31;
-    constexpr int I0 = W, I1 = NT - 1 - W;
-#pragma unroll
-    for (int j = 0; j < N0; ++j) {
-      *reinterpret_cast<double2*>(out + size_t(SM::gidx(I0, I0 + j)) * 64 + lane * 2) = make_double2(acc0[j][0], acc0[j][1]);
-    }
-#pragma unroll
-    for (int j = 0; j < N1; ++j) {
-      *reinterpret_cast<double2*>(out + size_t(SM::gidx(I1, I1 + j)) * 64 + lane * 2) = make_double2(acc1[j][0], acc1[j][1]);
-    }
-  }
-};
-
-template <int NT, int W>
-__device__ __forceinline__ void gram_dispatch(int warp, unsigned char* smem, const RowSource& rs, int64_t r0,
-                                              int64_t r1, double* out) {
+__device__ __forceinline__ void chunk_mma_dispatch(int warp, double (&acc)[NT + 1][2], const double* sb,
+                                                   const double* wt, int lane) {
   if constexpr (W < NT / 2) {
     if (warp == W) {
-      double csum;
-      build_warp<NT, W, false>(smem, rs, r0, r1, 0u, csum, GramEpilogue<NT, W>{out});
+      chunk_mma<NT, W>(acc, sb, wt, lane);
     } else {
-      gram_dispatch<NT, W + 1>(warp, smem, rs, r0, r1, out);
+      chunk_mma_dispatch<NT, W + 1>(warp, acc, sb, wt, lane);
     }
   }
 }
 
+// index (in the packed Gram / in the shared tile array) of this warp's t-th accumulator tile
+template <int NT>
+__device__ __forceinline__ void acc_tile(int warp, int t, int& I, int& J) {
+  const int n0 = NT - warp;
+  if (t < n0) {
+    I = warp;
+    J = warp + t;
+  } else {
+    I = NT - 1 - warp;
+    J = I + (t - n0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Gram kernel: partial upper-tile Gram of rows [r0, r1) per CTA (contiguous rows streamed by TMA
+// bulk copies, one per row), then a deterministic reduce
+// ------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(const double* __restrict__ Y, int64_t ldy,
                                                                               int64_t row_begin, int64_t row_end,
                                                                               double* __restrict__ partial) {
   using SM = WalsSmem<NT>;
   extern __shared__ __align__(128) unsigned char smem[];
+  double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
+  double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* empty = full + kStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
@@ -284,8 +209,41 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(co
   const int64_t n = row_end - row_begin;
   const int64_t r0 = row_begin + n * blockIdx.x / gridDim.x;
   const int64_t r1 = row_begin + n * (blockIdx.x + 1) / gridDim.x;
-  RowSource rs{Y, ldy, nullptr, nullptr, 0.0};
-  gram_dispatch<NT, 0>(threadIdx.x >> 5, smem, rs, r0, r1, partial + size_t(blockIdx.x) * SM::NTILE_A * 64);
+  const int nch = int((r1 - r0 + kChunk - 1) / kChunk);
+
+  auto issue = [&](int c) {  // warp 0 only
+    const uint32_t st = c % kStages;
+    if (c >= kStages) mbar_wait(&empty[st], ((c / kStages) & 1u) ^ 1u);
+    const int64_t p = r0 + int64_t(c) * kChunk + lane;
+    const bool valid = lane < kChunk && p < r1;
+    if (lane < kChunk) wts[st * 2 * kChunk + lane] = valid ? 1.0 : 0.0;
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(&full[st], uint32_t(kChunk) * SM::KP * 8);
+    __syncwarp();
+    if (lane < kChunk) bulk_g2s(stagebuf + (size_t(st) * kChunk + lane) * SM::LD, Y + (valid ? p : r0) * ldy, SM::KP * 8, &full[st]);
+  };
+
+  double acc[NT + 1][2];
+#pragma unroll
+  for (int t = 0; t <= NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+  if (warp == 0) {
+    for (int c = 0; c < nch && c < kStages - 1; ++c) issue(c);
+  }
+  for (int c = 0; c < nch; ++c) {
+    const uint32_t st = c % kStages;
+    if (warp == 0 && c + kStages - 1 < nch) issue(c + kStages - 1);
+    mbar_wait(&full[st], (c / kStages) & 1u);
+    chunk_mma_dispatch<NT, 0>(warp, acc, stagebuf + size_t(st) * kChunk * SM::LD, wts + st * 2 * kChunk, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+  double* out = partial + size_t(blockIdx.x) * SM::NTILE_A * 64;
+#pragma unroll
+  for (int t = 0; t <= NT; ++t) {
+    int I, J;
+    acc_tile<NT>(warp, t, I, J);
+    *reinterpret_cast<double2*>(out + size_t(SM::gidx(I, J)) * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
+  }
 }
 
 // out[t] = sum_b partial[b][t] in fixed order (deterministic), t over NTILE_A*64 packed entries
@@ -326,59 +284,13 @@ struct SolveParams {
   const double* gram;     // packed upper tiles of Y^T Y (all rows of Y)
   double alpha, lambda;
   double* row_loss;       // per local row loss term (WALSEngine.cpp:295-304)
-  int* counter;           // dynamic scheduler
   int* error;             // set to 1 if a pivot is not positive (reference: CHECK_EQ(result, 0), Matrix.cpp:94)
 };
 
-template <int NT, int W>
-struct SolveEpilogue {
-  unsigned char* smem;
-  const double* gram;
-  double lambda;
-  int k;
-  template <int N0, int N1>
-  __device__ __forceinline__ void operator()(double (&acc0)[N0][2], double (&acc1)[N1][2], double bacc) const {
-    using SM = WalsSmem<NT>;
-    const int lane = threadIdx.x & 31;
-    constexpr int I0 = W, I1 = NT - 1 - W;
-    // all warps must be done reading the staging ring before tiles (aliased) are written
-    reinterpret_cast<double*>(smem + SM::kOffBh)[threadIdx.x] = bacc;
-    __syncthreads();
-    double* tiles = reinterpret_cast<double*>(smem);
-    const int r = lane >> 2, c0 = 2 * (lane & 3);
-    auto put = [&](int I, int J, double (&a)[2]) {
-      const double2 g = *reinterpret_cast<const double2*>(gram + size_t(SM::gidx(I, J)) * 64 + lane * 2);
-      double v0 = a[0] + g.x, v1 = a[1] + g.y;
-      if (I == J) {  // A(i,i) += lambda (WALSEngine.cpp:290-292); padded dimensions get a unit pivot
-        const int gi = 8 * I + r;
-        if (c0 == r) v0 = gi < k ? v0 + lambda : 1.0;
-        if (c0 + 1 == r) v1 = gi < k ? v1 + lambda : 1.0;
-      }
-      *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(I, J)) * 64 + lane * 2) = make_double2(v0, v1);
-    };
-#pragma unroll
-    for (int j = 0; j < N0; ++j) put(I0, I0 + j, acc0[j]);
-#pragma unroll
-    for (int j = 0; j < N1; ++j) put(I1, I1 + j, acc1[j]);
-  }
-};
-
-template <int NT, int W>
-__device__ __forceinline__ void solve_build_dispatch(int warp, unsigned char* smem, const RowSource& rs, int64_t p0,
-                                                     int64_t p1, uint32_t chunk_base, double& csum,
-                                                     const SolveParams& prm) {
-  if constexpr (W < NT / 2) {
-    if (warp == W) {
-      build_warp<NT, W, true>(smem, rs, p0, p1, chunk_base, csum, SolveEpilogue<NT, W>{smem, prm.gram, prm.lambda, prm.k});
-    } else {
-      solve_build_dispatch<NT, W + 1>(warp, smem, rs, p0, p1, chunk_base, csum, prm);
-    }
-  }
-}
-
-// One warp: factor the 8x8 diagonal tile (upper Cholesky A = U^T U) in C-fragment layout with
-// shuffles and write W = inv(U) (row-major, upper) to wtile.  Returns false on a bad pivot.
-__device__ __forceinline__ bool factor_diag_tile(const double* tile, double* wtile, int lane) {
+// One warp: factor the 8x8 diagonal tile (upper Cholesky A = U^T U) in C-fragment layout (lane
+// holds row lane/4, columns 2*(lane%4)+{0,1}) with shuffles, eliminating an identity alongside,
+// and write W = inv(U) (row-major, upper) to wtile.  Returns false on a non-positive pivot.
+__device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile, int lane) {
   const int r = lane >> 2, q = lane & 3;
   double2 a = *reinterpret_cast<const double2*>(tile + lane * 2);
   double a0 = a.x, a1 = a.y;
@@ -410,11 +322,12 @@ __device__ __forceinline__ bool factor_diag_tile(const double* tile, double* wti
 }
 
 template <int NT>
-__global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >= 8 ? 4 : 8)))
-  wals_solve_kernel(const SolveParams prm) {
+__global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, 1) wals_solve_kernel(const SolveParams prm) {
   using SM = WalsSmem<NT>;
   extern __shared__ __align__(128) unsigned char smem[];
-  double* tiles = reinterpret_cast<double*>(smem);
+  double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
+  double* tiles = reinterpret_cast<double*>(smem + SM::kOffTiles);
+  double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
   double* wt = reinterpret_cast<double*>(smem + SM::kOffW);
   double* bcopy = reinterpret_cast<double*>(smem + SM::kOffB);
   double* xvec = reinterpret_cast<double*>(smem + SM::kOffX);
@@ -422,34 +335,129 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
   double* bhalf = reinterpret_cast<double*>(smem + SM::kOffBh);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* empty = full + kStages;
-  int* misc = reinterpret_cast<int*>(smem + SM::kOffMisc);
+  unsigned short* tmap = reinterpret_cast<unsigned short*>(smem + SM::kOffMap);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  constexpr int TPR = SM::KP / 2;  // threads per gathered row (16 bytes each); 4 rows per pass
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], SM::NTHREADS + kChunk);  // one deferred cp.async arrival per thread + weight writers
       mbar_init(&empty[s], SM::NWARPS);
     }
     mbar_fence_init();
   }
-  uint32_t chunk_base = 0;
-  RowSource rs{prm.Y, prm.ldy, prm.col, prm.val, prm.alpha};
+  // (J1, J2) of every packed tile: the trailing set of panel I is the contiguous range [tidx(I+1,I+1), NTILE)
+  for (int I = tid; I < NT; I += SM::NTHREADS) {
+    for (int J = I; J <= NT; ++J) tmap[SM::tidx(I, J)] = static_cast<unsigned short>((I << 8) | J);
+  }
 
-  for (;;) {
-    __syncthreads();  // previous row fully retired (tiles, xvec, misc free)
-    if (tid == 0) misc[0] = atomicAdd(prm.counter, 1);
-    fence_proxy_async();  // order this row's generic writes to the aliased ring before the next bulk copies
+  // ---- static serpentine schedule over the longest-first order ---------------------------------
+  const int G = gridDim.x, bid = blockIdx.x;
+  auto slot_of = [&](int i) { return i * G + ((i & 1) ? (G - 1 - bid) : bid); };
+  struct Row { int row; int64_t p0, p1; int nch; };
+  auto fetch = [&](int i) {
+    Row r{-1, 0, 0, 0};
+    const int s = slot_of(i);
+    if (s < prm.nrows) {
+      r.row = __ldg(prm.order + s);
+      r.p0 = __ldg(prm.row_ptr + r.row);
+      r.p1 = __ldg(prm.row_ptr + r.row + 1);
+      r.nch = int((r.p1 - r.p0 + kChunk - 1) / kChunk);
+    }
+    return r;
+  };
+  int it = 0;
+  Row cur = fetch(0), nxt = fetch(1);
+
+  // ---- gather pipeline state (uniform across the CTA) ---------------------------------------------
+  uint32_t base = 0;      // absolute chunk index of cur's chunk 0
+  uint32_t issued = 0;    // absolute index of the next chunk to issue (cur's, then nxt's)
+  int32_t pcol = 0;       // lanes < kChunk: column of row `lane` of chunk `issued`
+  double pval = 0.0;      // warp 0, lanes < kChunk: its rating
+  bool pvalid = false;
+  double csum_cur = 0.0, csum_nxt = 0.0;
+  auto prefetch_idx = [&]() {  // registers for chunk `issued`
+    const uint32_t rel = issued - base;
+    const bool in_cur = rel < uint32_t(cur.nch);
+    const int64_t q0 = in_cur ? cur.p0 : nxt.p0, q1 = in_cur ? cur.p1 : nxt.p1;
+    const int64_t p = q0 + int64_t(in_cur ? rel : rel - cur.nch) * kChunk + lane;
+    pvalid = lane < kChunk && p < q1 && (in_cur || rel - cur.nch < uint32_t(nxt.nch));
+    pcol = pvalid ? __ldg(prm.col + p) : 0;
+    pval = (pvalid && tid < kChunk) ? __ldg(prm.val + p) : 0.0;
+  };
+  auto issue_one = [&]() {
+    const uint32_t st = issued % kStages;
+    if (issued >= kStages) mbar_wait(&empty[st], ((issued / kStages) & 1u) ^ 1u);
+    if (tid < kChunk) {
+      const double wa = pvalid ? prm.alpha * pval : 0.0;        // WALSEngine.cpp:282  alpha * r
+      const double wb = pvalid ? 1.0 + prm.alpha * pval : 0.0;  // WALSEngine.cpp:280  1 + alpha * r
+      wts[st * 2 * kChunk + lane] = wa;
+      wts[st * 2 * kChunk + kChunk + lane] = wb;
+      if (issued - base < uint32_t(cur.nch)) csum_cur += wb; else csum_nxt += wb;
+      mbar_arrive(&full[st]);
+    }
+    const int rsub = tid / TPR, piece = tid % TPR;
+#pragma unroll
+    for (int m = 0; m < kChunk / 4; ++m) {
+      const int row = 4 * m + rsub;
+      const int32_t c = __shfl_sync(0xffffffffu, pcol, row);
+      cp_async16(stagebuf + (size_t(st) * kChunk + row) * SM::LD + piece * 2, prm.Y + int64_t(c) * prm.ldy + piece * 2);
+    }
+    cp_async_arrive(&full[st]);
+    ++issued;
+    prefetch_idx();
+  };
+  prefetch_idx();
+  __syncthreads();  // barriers initialised
+
+  const int fo = (lane & 3) * 8 + (lane >> 2);  // fragment offset inside a tile (see tile_mma_tn)
+  while (cur.row >= 0) {
+    Row nn = fetch(it + 2);  // the row after next: its index loads fly during this row
+    // ---- build ------------------------------------------------------------------------------------
+    double acc[NT + 1][2];
+#pragma unroll
+    for (int t = 0; t <= NT; ++t) {  // accumulators start from the Gram tiles
+      int I, J;
+      acc_tile<NT>(warp, t, I, J);
+      const double2 g = *reinterpret_cast<const double2*>(prm.gram + size_t(SM::gidx(I, J)) * 64 + lane * 2);
+      acc[t][0] = g.x;
+      acc[t][1] = g.y;
+    }
+    double bacc = 0.0;
+    const int bi = tid % SM::KP, bh = tid / SM::KP;
+    const uint32_t lim = base + uint32_t(cur.nch) + uint32_t(nxt.nch);
+    for (int c = 0; c < cur.nch; ++c) {
+      const uint32_t gc = base + c;
+      while (issued < lim && issued < gc + kStages) issue_one();
+      const uint32_t st = gc % kStages;
+      mbar_wait(&full[st], (gc / kStages) & 1u);
+      const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
+      const double* w8 = wts + st * 2 * kChunk;
+      chunk_mma_dispatch<NT, 0>(warp, acc, sb, w8, lane);
+#pragma unroll
+      for (int s = 0; s < kChunk / 2; ++s) bacc += w8[kChunk + 2 * s + bh] * sb[(2 * s + bh) * SM::LD + bi];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    while (issued < lim && issued < base + cur.nch + kStages) issue_one();  // keep the ring full of nxt's chunks
+    // ---- tiles to shared memory: A(i,i) += lambda (WALSEngine.cpp:290-292), unit pivot on padding -----
+    {
+      const int r = lane >> 2, c0 = 2 * (lane & 3);
+#pragma unroll
+      for (int t = 0; t <= NT; ++t) {
+        int I, J;
+        acc_tile<NT>(warp, t, I, J);
+        double v0 = acc[t][0], v1 = acc[t][1];
+        if (I == J) {
+          const int gi = 8 * I + r;
+          if (c0 == r) v0 = gi < prm.k ? v0 + prm.lambda : 1.0;
+          if (c0 + 1 == r) v1 = gi < prm.k ? v1 + prm.lambda : 1.0;
+        }
+        *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(I, J)) * 64 + lane * 2) = make_double2(v0, v1);
+      }
+      bhalf[tid] = bacc;
+    }
     __syncthreads();
-    const int slot = misc[0];
-    if (slot >= prm.nrows) break;
-    const int row = prm.order[slot];
-    const int64_t p0 = prm.row_ptr[row], p1 = prm.row_ptr[row + 1];
-    const int nch = int((p1 - p0 + kChunk - 1) / kChunk);
-
-    // ---- build: accumulators -> (+ Gram, + lambda) -> tiles in shared memory ------------------
-    double csum = 0.0;
-    solve_build_dispatch<NT, 0>(warp, smem, rs, p0, p1, chunk_base, csum, prm);
-    chunk_base += uint32_t(nch);
     // b = sum of the two half sums; b column tiles (column 0 = b, other columns 0); keep a copy
     if (tid < SM::KP) {
       const double b = bhalf[tid] + bhalf[tid + SM::KP];
@@ -459,102 +467,141 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
 #pragma unroll
       for (int c = 1; c < 8; ++c) bt[c] = 0.0;
     }
-    __syncthreads();
-
     // ---- blocked Cholesky, panel width 8; forward substitution rides along in column NT ------
     bool ok = true;
     if (warp == 0) ok = factor_diag_tile(tiles + size_t(SM::tidx(0, 0)) * 64, wt, lane);
     for (int I = 0; I < NT; ++I) {
       __syncthreads();  // W_I ready, row I of tiles final up to panel I-1
       // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+1 .. NT
-      for (int J = I + 1 + warp; J <= NT; J += SM::NWARPS) {
-        double* t = tiles + size_t(SM::tidx(I, J)) * 64;
-        double c[2] = {0.0, 0.0};
-        tile_mma_tn(c, wt + I * 64, t, lane, 1.0);
-        __syncwarp();
-        *reinterpret_cast<double2*>(t + lane * 2) = make_double2(c[0], c[1]);
+      {
+        const double w0 = wt[I * 64 + fo], w1 = wt[I * 64 + fo + 32];
+        for (int J = I + 1 + warp; J <= NT; J += SM::NWARPS) {
+          double* t = tiles + size_t(SM::tidx(I, J)) * 64;
+          double c[2] = {0.0, 0.0};
+          dmma(c, w0, t[fo]);
+          dmma(c, w1, t[fo + 32]);
+          __syncwarp();
+          *reinterpret_cast<double2*>(t + lane * 2) = make_double2(c[0], c[1]);
+        }
       }
       if (I == NT - 1) break;
       __syncthreads();
       // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT.
-      //     The warp that owns the next diagonal tile updates it first and factors it right away
-      //     (look-ahead) while the other warps sweep the rest.
-      const int T = NT - 1 - I;               // rows J1 = I+1 .. NT-1
-      const int ntr = T * (T + 1) / 2 + T;    // tiles incl. b column
-      const int dwarp = (I + 1) % SM::NWARPS;
+      //     One warp updates the next diagonal tile first and factors it right away (look-ahead)
+      //     while the other warps sweep the rest, four independent tiles at a time.
+      const int tstart = SM::tidx(I + 1, I + 1);
+      const double* urow = tiles + size_t(SM::tidx(I, I)) * 64;  // tile (I, J) = urow + (J - I) * 64
+      constexpr int dwarp = 0;
       const int nw = SM::NWARPS > 1 ? SM::NWARPS - 1 : 1;
-      const int wslot = SM::NWARPS > 1 ? (warp > dwarp ? warp - 1 : warp) : 0;
+      const int wslot = SM::NWARPS > 1 ? warp - 1 : 0;
       if (SM::NWARPS == 1 || warp == dwarp) {
-        double* t = tiles + size_t(SM::tidx(I + 1, I + 1)) * 64;
-        const double* u = tiles + size_t(SM::tidx(I, I + 1)) * 64;
+        double* t = tiles + size_t(tstart) * 64;
+        const double* u = urow + 64;
         double2 cv = *reinterpret_cast<double2*>(t + lane * 2);
         double c[2] = {cv.x, cv.y};
-        tile_mma_tn(c, u, u, lane, -1.0);
+        const double u0 = u[fo], u1 = u[fo + 32];
+        dmma(c, -u0, u0);
+        dmma(c, -u1, u1);
         *reinterpret_cast<double2*>(t + lane * 2) = make_double2(c[0], c[1]);
         __syncwarp();
         ok = factor_diag_tile(t, wt + (I + 1) * 64, lane) && ok;
       }
       if (SM::NWARPS == 1 || warp != dwarp) {
-        // linear tile index e in [1, ntr): row J1 has (NT - J1 + 1) tiles; e == 0 is the diagonal tile above
-        int J1 = I + 1, base = 0;
-        for (int e = 1 + wslot; e < ntr; e += nw) {
-          while (e - base >= NT - J1 + 1) {
-            base += NT - J1 + 1;
-            ++J1;
+        for (int e = tstart + 1 + wslot; e < SM::NTILE; e += 4 * nw) {
+          double c[4][2], ua[4][2], ub[4][2];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int ti = e + q * nw;
+            if (ti < SM::NTILE) {
+              const int jj = tmap[ti];
+              const double* ta = urow + ((jj >> 8) - I) * 64;
+              const double* tb = urow + ((jj & 255) - I) * 64;
+              const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(ti) * 64 + lane * 2);
+              c[q][0] = cv.x; c[q][1] = cv.y;
+              ua[q][0] = -ta[fo]; ua[q][1] = -ta[fo + 32];
+              ub[q][0] = tb[fo]; ub[q][1] = tb[fo + 32];
+            }
           }
-          const int J2 = J1 + (e - base);
-          double* t = tiles + size_t(SM::tidx(J1, J2)) * 64;
-          double2 cv = *reinterpret_cast<double2*>(t + lane * 2);
-          double c[2] = {cv.x, cv.y};
-          tile_mma_tn(c, tiles + size_t(SM::tidx(I, J1)) * 64, tiles + size_t(SM::tidx(I, J2)) * 64, lane, -1.0);
-          *reinterpret_cast<double2*>(t + lane * 2) = make_double2(c[0], c[1]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (e + q * nw < SM::NTILE) {
+              dmma(c[q], ua[q][0], ub[q][0]);
+              dmma(c[q], ua[q][1], ub[q][1]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int ti = e + q * nw;
+            if (ti < SM::NTILE) *reinterpret_cast<double2*>(tiles + size_t(ti) * 64 + lane * 2) = make_double2(c[q][0], c[q][1]);
+          }
         }
       }
     }
     if (!ok && lane == 0) *prm.error = 1;
-    __syncthreads();
 
-    // ---- back substitution U x = z (warp 0), loss, store ----------------------------------------
-    if (warp == 0) {
-      for (int i = lane; i < SM::KP; i += 32) rvec[i] = tiles[size_t(SM::tidx(i >> 3, NT)) * 64 + (i & 7) * 8];
-      __syncwarp();
-      for (int I = NT - 1; I >= 0; --I) {
-        if (lane < 8) {  // x_I = W_I * r_I (W upper triangular)
-          const double* w = wt + I * 64 + lane * 8;
-          double s0 = 0.0, s1 = 0.0;
+    // ---- back substitution U x = z: thread t < KP keeps r_t in a register; per block step one
+    //      8x8 mat-vec by inv(U_JJ) and one rank-8 update of the rows above -----------------------
+    __syncthreads();
+    double r = 0.0;
+    if (tid < SM::KP) {
+      r = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8];
+      if ((tid >> 3) == NT - 1) rvec[tid & 7] = r;
+    }
+    for (int J = NT - 1; J >= 0; --J) {
+      __syncthreads();
+      if ((tid >> 3) == J) {  // x_J = W_J * r_J
+        const double* w = wt + J * 64 + (tid & 7) * 8;
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int c = 0; c < 8; c += 2) {
-            s0 += w[c] * rvec[8 * I + c];
-            s1 += w[c + 1] * rvec[8 * I + c + 1];
-          }
-          xvec[8 * I + lane] = s0 + s1;
+        for (int c = 0; c < 8; c += 2) {
+          s0 += w[c] * rvec[c];
+          s1 += w[c + 1] * rvec[c + 1];
         }
-        __syncwarp();
-        // r_J -= U[J][I] x_I for J < I: one tile per iteration, lane reads its C-fragment pair
-        const double x0 = xvec[8 * I + 2 * (lane & 3)], x1 = xvec[8 * I + 2 * (lane & 3) + 1];
-        for (int J = 0; J < I; ++J) {
-          const double2 u = *reinterpret_cast<const double2*>(tiles + size_t(SM::tidx(J, I)) * 64 + lane * 2);
-          double pr = u.x * x0 + u.y * x1;
-          pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-          pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-          if ((lane & 3) == 0) rvec[8 * J + (lane >> 2)] -= pr;
-        }
-        __syncwarp();
+        xvec[tid] = s0 + s1;
       }
-      // loss term: c + x^T B x - 2 x^T b with x^T B x = z^T z - lambda x^T x (WALSEngine.cpp:295-304)
+      if (J == 0) break;
+      __syncthreads();
+      if (tid < 8 * J) {  // r_t -= U[t][8J .. 8J+7] . x_J
+        const double* u = tiles + size_t(SM::tidx(tid >> 3, J)) * 64 + (tid & 7) * 8;
+        const double* x = xvec + 8 * J;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          const int cr = (c + 2 * (tid & 3)) & 7;  // rotate the start column to spread banks
+          const double2 uv = *reinterpret_cast<const double2*>(u + cr);
+          s0 += uv.x * x[cr];
+          s1 += uv.y * x[cr + 1];
+        }
+        r -= s0 + s1;
+        if ((tid >> 3) == J - 1) rvec[tid & 7] = r;
+      }
+    }
+    __syncthreads();
+    // ---- loss term: c + x^T B x - 2 x^T b with x^T B x = z^T z - lambda x^T x (WALSEngine.cpp:295-304)
+    if (warp == 0) {
       double part = 0.0;
       for (int i = lane; i < prm.k; i += 32) {
         const double z = tiles[size_t(SM::tidx(i >> 3, NT)) * 64 + (i & 7) * 8];
         const double x = xvec[i];
         part += z * z - prm.lambda * x * x - 2.0 * x * bcopy[i];
       }
-      part += csum;
+      part += csum_cur;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == 0) prm.row_loss[row] = part;
-      double* xr = prm.X + (prm.row_offset + row) * prm.ldx;
+      if (lane == 0) prm.row_loss[cur.row] = part;
+    } else if (warp == 1 || SM::NWARPS == 1) {
+      double* xr = prm.X + (prm.row_offset + cur.row) * prm.ldx;
       for (int i = lane; i < SM::KP; i += 32) xr[i] = i < prm.k ? xvec[i] : 0.0;
     }
+    // ---- next row -----------------------------------------------------------------------------------
+    base += uint32_t(cur.nch);
+    csum_cur = csum_nxt;
+    csum_nxt = 0.0;
+    cur = nxt;
+    nxt = nn;
+    ++it;
+    prefetch_idx();   // the registers for chunk `issued` were computed in the previous row's frame
+    __syncthreads();  // tiles / xvec / bcopy free again
   }
 }
 
