@@ -20,11 +20,10 @@
 //    shared memory, where a blocked right-looking Cholesky (8-wide panels, DMMA trailing
 //    updates, look-ahead on the diagonal tile, b carried as an extra tile column so the forward
 //    solve is free) and a blocked back substitution produce x.  A never leaves the SM.
-//  * One persistent CTA per SM at k=128: build (DMMA-bound) and solve (latency-bound) phases
-//    alternate instead of overlapping, because FP64 scalar ops of a solving CTA starve behind a
-//    co-resident CTA's DMMAs on the shared FP64 pipe (profiles/r01_solve_v1/v2).  The staging
-//    ring is separate from the tile storage, so the next row's first chunks are already in
-//    flight while the current row is being solved.
+//  * Two persistent CTAs per SM at k=128 (tile storage aliases the staging ring): while one CTA
+//    is in its latency-bound solve phase the other keeps the DMMA pipe busy building.  The solve
+//    phase is written for a short FP64 dependency chain (fraction-free 8x8 pivot block, see
+//    factor_diag_tile) because its scalar FP64 ops queue behind the other CTA's DMMAs.
 //  * Rows are sorted longest-first and dealt to the CTAs in serpentine order (static schedule,
 //    so the next row is known early enough to prefetch).
 #pragma once
@@ -36,7 +35,7 @@
 namespace qmfb {
 
 constexpr int kChunk = 16;   // gathered rows per pipeline stage
-constexpr int kStages = 7;   // ring depth (chunks in flight, may span two consecutive rows)
+constexpr int kStages = 4;   // ring depth
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers
@@ -115,17 +114,17 @@ struct WalsSmem {
   static constexpr int NTILE = NTILE_A + NT;    // + one tile column for b
   static constexpr size_t kStageBytes = size_t(kStages) * kChunk * LD * 8;
   static constexpr size_t kTileBytes = size_t(NTILE) * 64 * 8;
+  static constexpr size_t kMainBytes = kStageBytes > kTileBytes ? kStageBytes : kTileBytes;
   static constexpr size_t kOffStage = 0;
-  static constexpr size_t kOffTiles = kStageBytes;
-  static constexpr size_t kOffWts = kOffTiles + kTileBytes;                  // kStages*2*kChunk doubles
+  static constexpr size_t kOffTiles = 0;                                     // aliases the staging ring
+  static constexpr size_t kOffWts = kMainBytes;                              // kStages*2*kChunk doubles
   static constexpr size_t kOffW = kOffWts + size_t(kStages) * 2 * kChunk * 8;  // NT inverse diagonal tiles
   static constexpr size_t kOffB = kOffW + size_t(NT) * 64 * 8;               // b copy (KP)
   static constexpr size_t kOffX = kOffB + size_t(KP) * 8;                    // x (KP)
   static constexpr size_t kOffR = kOffX + size_t(KP) * 8;                    // back-substitution rhs (8)
   static constexpr size_t kOffBh = kOffR + 64;                               // b half sums (2*KP)
   static constexpr size_t kOffBar = kOffBh + size_t(KP) * 16;                // full[kStages], empty[kStages]
-  static constexpr size_t kOffMap = kOffBar + size_t(kStages) * 16;          // (J1,J2) of every tile, 2 bytes each
-  static constexpr size_t kBytes = kOffMap + ((size_t(NTILE) * 2 + 15) / 16) * 16;
+  static constexpr size_t kBytes = kOffBar + size_t(kStages) * 16;
 
   // tile (I,J), I <= J <= NT (J == NT is the b column), row-major upper storage
   __host__ __device__ static constexpr int tidx(int I, int J) { return I * (NT + 1) - I * (I - 1) / 2 + (J - I); }
@@ -287,42 +286,54 @@ struct SolveParams {
   int* error;             // set to 1 if a pivot is not positive (reference: CHECK_EQ(result, 0), Matrix.cpp:94)
 };
 
-// One warp: factor the 8x8 diagonal tile (upper Cholesky A = U^T U) in C-fragment layout (lane
-// holds row lane/4, columns 2*(lane%4)+{0,1}) with shuffles, eliminating an identity alongside,
-// and write W = inv(U) (row-major, upper) to wtile.  Returns false on a non-positive pivot.
+// One warp: factor the 8x8 diagonal tile A = U^T U and write W = inv(U) (row-major, upper) to
+// wtile.  C-fragment layout: lane holds row lane/4, columns 2*(lane%4)+{0,1}; an identity is
+// eliminated alongside.  The elimination is FRACTION-FREE so that the pivot-to-pivot dependency
+// chain is one shuffle + three FP64 ops instead of a reciprocal/rsqrt sequence:
+//     a_rc <- a_rc * pn - (a_jr * a_jc) * 2^-e,   p = a_jj = pn * 2^e, pn in [1, 2)
+// which keeps every remaining row scaled by S = prod(pn) (<= 2^8; the power-of-two factors are
+// exact).  Row r of the true factor is recovered at the end with a single
+// g_r = rsqrt(p_r * S_r):  U[r][c] = a_rc * g_r,  inv(U)[c][r] = e_rc * g_r.
+// Returns false on a non-positive pivot (reference: dsysv info != 0, qmf/Matrix.cpp:94).
 __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile, int lane) {
   const int r = lane >> 2, q = lane & 3;
-  double2 a = *reinterpret_cast<const double2*>(tile + lane * 2);
+  const double2 a = *reinterpret_cast<const double2*>(tile + lane * 2);
   double a0 = a.x, a1 = a.y;
   double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
+  double S = 1.0, prS = 1.0;
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const double piv = __shfl_sync(0xffffffffu, (j & 1) ? a1 : a0, 4 * j + (j >> 1));
-    ok = ok && (piv > 0.0);
-    const double d = rsqrt(piv);
-    if (r == j) {
-      a0 *= d; a1 *= d; e0 *= d; e1 *= d;
-    }
-    const double uc0 = __shfl_sync(0xffffffffu, a0, 4 * j + q);
-    const double uc1 = __shfl_sync(0xffffffffu, a1, 4 * j + q);
-    const double ec0 = __shfl_sync(0xffffffffu, e0, 4 * j + q);
-    const double ec1 = __shfl_sync(0xffffffffu, e1, 4 * j + q);
-    const double t0 = __shfl_sync(0xffffffffu, a0, 4 * j + (r >> 1));
-    const double t1 = __shfl_sync(0xffffffffu, a1, 4 * j + (r >> 1));
+    const int src = 4 * j;
+    const double p = __shfl_sync(0xffffffffu, (j & 1) ? a1 : a0, src + (j >> 1));
+    const double uc0 = __shfl_sync(0xffffffffu, a0, src + q);
+    const double uc1 = __shfl_sync(0xffffffffu, a1, src + q);
+    const double ec0 = __shfl_sync(0xffffffffu, e0, src + q);
+    const double ec1 = __shfl_sync(0xffffffffu, e1, src + q);
+    const double t0 = __shfl_sync(0xffffffffu, a0, src + (r >> 1));
+    const double t1 = __shfl_sync(0xffffffffu, a1, src + (r >> 1));
     const double ur = (r & 1) ? t1 : t0;
+    ok = ok && (p > 0.0);
+    const int hi = __double2hiint(p), lo = __double2loint(p);
+    const double pn = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, lo);
+    const double sc = __hiloint2double((2046 - ((hi >> 20) & 0x7ff)) << 20, 0);
+    if (r == j) prS = p * S;
+    S *= pn;
     if (r > j) {
-      a0 -= ur * uc0; a1 -= ur * uc1; e0 -= ur * ec0; e1 -= ur * ec1;
+      a0 = fma(a0, pn, -((ur * uc0) * sc));
+      a1 = fma(a1, pn, -((ur * uc1) * sc));
+      e0 = fma(e0, pn, -((ur * ec0) * sc));
+      e1 = fma(e1, pn, -((ur * ec1) * sc));
     }
   }
-  // e = inv(U)^T (lower triangular); store W = e^T
-  wtile[(2 * q) * 8 + r] = e0;
-  wtile[(2 * q + 1) * 8 + r] = e1;
+  const double g = rsqrt(prS);
+  wtile[(2 * q) * 8 + r] = e0 * g;
+  wtile[(2 * q + 1) * 8 + r] = e1 * g;
   return ok;
 }
 
 template <int NT>
-__global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, 1) wals_solve_kernel(const SolveParams prm) {
+__global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >= 8 ? 4 : 8))) wals_solve_kernel(const SolveParams prm) {
   using SM = WalsSmem<NT>;
   extern __shared__ __align__(128) unsigned char smem[];
   double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
@@ -335,7 +346,6 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, 1) wals_solve_kernel(c
   double* bhalf = reinterpret_cast<double*>(smem + SM::kOffBh);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* empty = full + kStages;
-  unsigned short* tmap = reinterpret_cast<unsigned short*>(smem + SM::kOffMap);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   constexpr int TPR = SM::KP / 2;  // threads per gathered row (16 bytes each); 4 rows per pass
 
@@ -345,10 +355,6 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, 1) wals_solve_kernel(c
       mbar_init(&empty[s], SM::NWARPS);
     }
     mbar_fence_init();
-  }
-  // (J1, J2) of every packed tile: the trailing set of panel I is the contiguous range [tidx(I+1,I+1), NTILE)
-  for (int I = tid; I < NT; I += SM::NTHREADS) {
-    for (int J = I; J <= NT; ++J) tmap[SM::tidx(I, J)] = static_cast<unsigned short>((I << 8) | J);
   }
 
   // ---- static serpentine schedule over the longest-first order ---------------------------------
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, 1) wals_solve_kernel(c
     }
     double bacc = 0.0;
     const int bi = tid % SM::KP, bh = tid / SM::KP;
-    const uint32_t lim = base + uint32_t(cur.nch) + uint32_t(nxt.nch);
+    const uint32_t lim = base + uint32_t(cur.nch);  // the ring is reused as tile storage: no cross-row prefetch
     for (int c = 0; c < cur.nch; ++c) {
       const uint32_t gc = base + c;
       while (issued < lim && issued < gc + kStages) issue_one();
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, 1) wals_solve_kernel(c
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
     }
-    while (issued < lim && issued < base + cur.nch + kStages) issue_one();  // keep the ring full of nxt's chunks
+    __syncthreads();  // every warp is done reading the ring before the tiles overwrite it
     // ---- tiles to shared memory: A(i,i) += lambda (WALSEngine.cpp:290-292), unit pivot on padding -----
     {
       const int r = lane >> 2, c0 = 2 * (lane & 3);
@@ -507,19 +513,25 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, 1) wals_solve_kernel(c
         ok = factor_diag_tile(t, wt + (I + 1) * 64, lane) && ok;
       }
       if (SM::NWARPS == 1 || warp != dwarp) {
+        // flat enumeration of the trailing tiles (contiguous in storage); (J1, J2) decoded incrementally
+        int J1 = I + 1, off = 1 + wslot;  // position `off` inside row J1 (row J1 has NT - J1 + 1 tiles)
         for (int e = tstart + 1 + wslot; e < SM::NTILE; e += 4 * nw) {
           double c[4][2], ua[4][2], ub[4][2];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int ti = e + q * nw;
             if (ti < SM::NTILE) {
-              const int jj = tmap[ti];
-              const double* ta = urow + ((jj >> 8) - I) * 64;
-              const double* tb = urow + ((jj & 255) - I) * 64;
+              while (off >= NT - J1 + 1) {
+                off -= NT - J1 + 1;
+                ++J1;
+              }
+              const double* ta = urow + (J1 - I) * 64;
+              const double* tb = urow + (J1 + off - I) * 64;
               const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(ti) * 64 + lane * 2);
               c[q][0] = cv.x; c[q][1] = cv.y;
               ua[q][0] = -ta[fo]; ua[q][1] = -ta[fo + 32];
               ub[q][0] = tb[fo]; ub[q][1] = tb[fo + 32];
+              off += nw;
             }
           }
 #pragma unroll
