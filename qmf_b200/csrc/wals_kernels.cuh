@@ -10,7 +10,7 @@
 //    shared-memory-fed loop below reaches ~35 TFLOP/s in isolation.
 //  * A row's k x k system is held as the upper triangle of 8x8 tiles.  Warp w of a CTA owns
 //    tile-rows w and NT-1-w (NT+1 tiles -> perfectly balanced), accumulators live in registers.
-//  * Factor rows are staged into padded shared memory (row stride KP+8 doubles -> conflict-free
+//  * Factor rows are staged into padded shared memory (row stride KP+4 doubles -> conflict-free
 //    DMMA fragment loads) through an mbarrier-tracked ring, no register staging.  Gathered rows
 //    (solve kernel) use 16-byte cp.async (LDGSTS) issued by all threads: the TMA engine's
 //    outstanding-request window caps a DRAM-resident 1 KB-row gather at ~5 B/clk/SM
@@ -31,6 +31,7 @@
 #include <stdint.h>
 
 #include <type_traits>
+#include <utility>
 
 namespace qmfb {
 
@@ -106,7 +107,11 @@ __device__ __forceinline__ void tile_mma_tn(double (&c)[2], const double* ta, co
 template <int NT>
 struct WalsSmem {
   static constexpr int KP = NT * 8;            // padded factor dimension
-  static constexpr int LD = KP + 8;            // staging row stride (doubles); LD % 16 == 8
+  // staging row stride (doubles).  A 64-bit shared load is served per half-warp (16 lanes x 8 B =
+  // one 128-byte wavefront); the DMMA fragment address is (lane%4)*LD + lane/4, so LD % 16 == 4
+  // gives 16 distinct bank pairs per half-warp (LD % 16 == 8 costs two wavefronts per half-warp:
+  // measured 41 % conflict wavefronts, profiles/r01_build_v4).
+  static constexpr int LD = KP + 4;
   static constexpr int NWARPS = NT / 2;
   static constexpr int NTHREADS = NWARPS * 32;  // == 2 * KP
   static constexpr int NACC = NT + 1;           // tiles per warp (rows w and NT-1-w)
@@ -124,7 +129,8 @@ struct WalsSmem {
   static constexpr size_t kOffR = kOffX + size_t(KP) * 8;                    // back-substitution rhs (8)
   static constexpr size_t kOffBh = kOffR + 64;                               // b half sums (2*KP)
   static constexpr size_t kOffBar = kOffBh + size_t(KP) * 16;                // full[kStages], empty[kStages]
-  static constexpr size_t kBytes = kOffBar + size_t(kStages) * 16;
+  static constexpr size_t kOffRow = kOffBar + size_t(kStages) * 16;          // 2 row slots x 32 bytes
+  static constexpr size_t kBytes = kOffRow + 64;
 
   // tile (I,J), I <= J <= NT (J == NT is the b column), row-major upper storage
   __host__ __device__ static constexpr int tidx(int I, int J) { return I * (NT + 1) - I * (I - 1) / 2 + (J - I); }
@@ -133,12 +139,13 @@ struct WalsSmem {
 };
 
 // ------------------------------------------------------------------------------------------
-// DMMA inner loop of one staged chunk for warp role W: tile rows I0 = W (NT-W tiles) and
-// I1 = NT-1-W (W+1 tiles); acc[0..N0) are row I0, acc[N0..NT+1) row I1.  This is the only code
-// that differs between warps; everything else in the kernels is a single copy.
+// DMMA inner loop of one staged chunk for warp role W (each warp owns NT+1 of the upper tiles).
+// This is the only code that differs between warps; everything else is a single copy.
 // ------------------------------------------------------------------------------------------
+// Row-pair tiling: warp W owns tile rows I0 = W (NT-W tiles) and I1 = NT-1-W (W+1 tiles);
+// acc[0..N0) are row I0, acc[N0..NT+1) row I1.
 template <int NT, int W>
-__device__ __forceinline__ void chunk_mma(double (&acc)[NT + 1][2], const double* sb, const double* wt, int lane) {
+__device__ __forceinline__ void chunk_mma_rows(double (&acc)[NT + 1][2], const double* sb, const double* wt, int lane) {
   using SM = WalsSmem<NT>;
   constexpr int I0 = W, I1 = NT - 1 - W, N0 = NT - I0, N1 = NT - I1, D = I1 - I0;
 #pragma unroll
@@ -158,6 +165,11 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[NT + 1][2], const double
 }
 
 template <int NT, int W>
+__device__ __forceinline__ void chunk_mma(double (&acc)[NT + 1][2], const double* sb, const double* wt, int lane) {
+  chunk_mma_rows<NT, W>(acc, sb, wt, lane);
+}
+
+template <int NT, int W>
 __device__ __forceinline__ void chunk_mma_dispatch(int warp, double (&acc)[NT + 1][2], const double* sb,
                                                    const double* wt, int lane) {
   if constexpr (W < NT / 2) {
@@ -169,7 +181,7 @@ __device__ __forceinline__ void chunk_mma_dispatch(int warp, double (&acc)[NT + 
   }
 }
 
-// index (in the packed Gram / in the shared tile array) of this warp's t-th accumulator tile
+// tile coordinates of this warp's t-th accumulator
 template <int NT>
 __device__ __forceinline__ void acc_tile(int warp, int t, int& I, int& J) {
   const int n0 = NT - warp;
@@ -332,6 +344,112 @@ __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile,
   return ok;
 }
 
+// Build phase of one row.  The kernel keeps its per-row schedule state in shared memory, so only
+// the accumulators and the loader state are live here; that leaves the register allocator room
+// to keep several DMMA fragments in flight under the 128-register cap of a 2-CTA/SM launch
+// (with ~25 more live registers ptxas serialises LDS -> DMMA -> LDS through one register).
+// Gathers rows col[p0..p1) of Y through the cp.async ring, accumulates
+//   A = G + sum_s (alpha r_s) y_s y_s^T   (upper tiles)      b = sum_s (1 + alpha r_s) y_s
+// (WALSEngine.cpp:277-287), adds lambda to the diagonal (:290-292) and leaves the tiles and the
+// two half sums of b in shared memory.  Returns this thread's share of sum_s (1 + alpha r_s).
+template <int NT>
+__device__ __forceinline__ double build_row(unsigned char* smem, const double* __restrict__ Y, int64_t ldy,
+                                         const int32_t* __restrict__ col, const double* __restrict__ val,
+                                         const double* __restrict__ gram, double alpha, double lambda, int k,
+                                         int64_t p0, int64_t p1, uint32_t base) {
+  using SM = WalsSmem<NT>;
+  double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
+  double* tiles = reinterpret_cast<double*>(smem + SM::kOffTiles);
+  double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
+  double* bhalf = reinterpret_cast<double*>(smem + SM::kOffBh);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
+  uint64_t* empty = full + kStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  constexpr int TPR = SM::KP / 2;  // threads per gathered row (16 bytes each); 4 rows per pass
+  const int nch = int((p1 - p0 + kChunk - 1) / kChunk);
+
+  uint32_t issued = base;  // absolute index of the next chunk to issue (stage = index % kStages)
+  int32_t pcol = 0;        // lanes < kChunk: column of row `lane` of chunk `issued`
+  double pval = 0.0;       // warp 0, lanes < kChunk: its rating
+  bool pvalid = false;
+  double csum = 0.0;       // warp 0, lanes < kChunk: sum of (1 + alpha r), WALSEngine.cpp:286
+  auto prefetch_idx = [&]() {
+    const int64_t p = p0 + int64_t(issued - base) * kChunk + lane;
+    pvalid = lane < kChunk && p < p1;
+    pcol = pvalid ? __ldg(col + p) : 0;
+    pval = (pvalid && tid < kChunk) ? __ldg(val + p) : 0.0;
+  };
+  auto issue_one = [&]() {
+    const uint32_t st = issued % kStages;
+    if (issued >= kStages) mbar_wait(&empty[st], ((issued / kStages) & 1u) ^ 1u);
+    if (tid < kChunk) {
+      const double wa = pvalid ? alpha * pval : 0.0;        // WALSEngine.cpp:282  alpha * r
+      const double wb = pvalid ? 1.0 + alpha * pval : 0.0;  // WALSEngine.cpp:280  1 + alpha * r
+      wts[st * 2 * kChunk + lane] = wa;
+      wts[st * 2 * kChunk + kChunk + lane] = wb;
+      csum += wb;
+      mbar_arrive(&full[st]);
+    }
+    const int rsub = tid / TPR, piece = tid % TPR;
+#pragma unroll
+    for (int m = 0; m < kChunk / 4; ++m) {
+      const int row = 4 * m + rsub;
+      const int32_t c = __shfl_sync(0xffffffffu, pcol, row);
+      cp_async16(stagebuf + (size_t(st) * kChunk + row) * SM::LD + piece * 2, Y + int64_t(c) * ldy + piece * 2);
+    }
+    cp_async_arrive(&full[st]);
+    ++issued;
+    prefetch_idx();
+  };
+  prefetch_idx();
+
+  double acc[NT + 1][2];
+#pragma unroll
+  for (int t = 0; t <= NT; ++t) {  // accumulators start from the Gram tiles
+    int I, J;
+    acc_tile<NT>(warp, t, I, J);
+    const double2 g = *reinterpret_cast<const double2*>(gram + size_t(SM::gidx(I, J)) * 64 + lane * 2);
+    acc[t][0] = g.x;
+    acc[t][1] = g.y;
+  }
+  double bacc = 0.0, bacc2 = 0.0;
+  const int bi = tid % SM::KP, bh = tid / SM::KP;
+  const uint32_t lim = base + uint32_t(nch);  // the ring is reused as tile storage: no cross-row prefetch
+  for (int c = 0; c < nch; ++c) {
+    const uint32_t gc = base + c;
+    while (issued < lim && issued < gc + kStages) issue_one();
+    const uint32_t st = gc % kStages;
+    mbar_wait(&full[st], (gc / kStages) & 1u);
+    const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
+    const double* w8 = wts + st * 2 * kChunk;
+    chunk_mma_dispatch<NT, 0>(warp, acc, sb, w8, lane);
+#pragma unroll
+    for (int s = 0; s < kChunk / 2; s += 2) {  // two independent chains
+      bacc += w8[kChunk + 2 * s + bh] * sb[(2 * s + bh) * SM::LD + bi];
+      bacc2 += w8[kChunk + 2 * s + 2 + bh] * sb[(2 * s + 2 + bh) * SM::LD + bi];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+  __syncthreads();  // every warp is done reading the ring before the tiles overwrite it
+  // tiles to shared memory: A(i,i) += lambda (WALSEngine.cpp:290-292), unit pivot on padding
+  const int r = lane >> 2, c0 = 2 * (lane & 3);
+#pragma unroll
+  for (int t = 0; t <= NT; ++t) {
+    int I, J;
+    acc_tile<NT>(warp, t, I, J);
+    double v0 = acc[t][0], v1 = acc[t][1];
+    if (I == J) {
+      const int gi = 8 * I + r;
+      if (c0 == r) v0 = gi < k ? v0 + lambda : 1.0;
+      if (c0 + 1 == r) v1 = gi < k ? v1 + lambda : 1.0;
+    }
+    *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(I, J)) * 64 + lane * 2) = make_double2(v0, v1);
+  }
+  bhalf[tid] = bacc + bacc2;
+  return csum;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >= 8 ? 4 : 8))) wals_solve_kernel(const SolveParams prm) {
   using SM = WalsSmem<NT>;
@@ -357,111 +475,44 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
     mbar_fence_init();
   }
 
-  // ---- static serpentine schedule over the longest-first order ---------------------------------
+  // ---- static serpentine schedule over the longest-first order; the per-row state lives in two
+  //      shared-memory slots (current / next) so that it costs no registers during the build ------
+  struct RowSlot {
+    int64_t p0, p1;
+    int32_t row;
+    uint32_t base;  // absolute chunk index of the row's chunk 0 (ring stage = index % kStages)
+    int64_t pad;
+  };
+  volatile RowSlot* slots = reinterpret_cast<volatile RowSlot*>(smem + SM::kOffRow);
   const int G = gridDim.x, bid = blockIdx.x;
   auto slot_of = [&](int i) { return i * G + ((i & 1) ? (G - 1 - bid) : bid); };
-  struct Row { int row; int64_t p0, p1; int nch; };
-  auto fetch = [&](int i) {
-    Row r{-1, 0, 0, 0};
-    const int s = slot_of(i);
-    if (s < prm.nrows) {
-      r.row = __ldg(prm.order + s);
-      r.p0 = __ldg(prm.row_ptr + r.row);
-      r.p1 = __ldg(prm.row_ptr + r.row + 1);
-      r.nch = int((r.p1 - r.p0 + kChunk - 1) / kChunk);
-    }
-    return r;
-  };
+  if (tid == 0) {
+    const int s0 = slot_of(0);
+    const int r0 = s0 < prm.nrows ? prm.order[s0] : -1;
+    slots[0].row = r0;
+    slots[0].base = 0u;
+    slots[0].p0 = r0 >= 0 ? prm.row_ptr[r0] : 0;
+    slots[0].p1 = r0 >= 0 ? prm.row_ptr[r0 + 1] : 0;
+  }
   int it = 0;
-  Row cur = fetch(0), nxt = fetch(1);
-
-  // ---- gather pipeline state (uniform across the CTA) ---------------------------------------------
-  uint32_t base = 0;      // absolute chunk index of cur's chunk 0
-  uint32_t issued = 0;    // absolute index of the next chunk to issue (cur's, then nxt's)
-  int32_t pcol = 0;       // lanes < kChunk: column of row `lane` of chunk `issued`
-  double pval = 0.0;      // warp 0, lanes < kChunk: its rating
-  bool pvalid = false;
-  double csum_cur = 0.0, csum_nxt = 0.0;
-  auto prefetch_idx = [&]() {  // registers for chunk `issued`
-    const uint32_t rel = issued - base;
-    const bool in_cur = rel < uint32_t(cur.nch);
-    const int64_t q0 = in_cur ? cur.p0 : nxt.p0, q1 = in_cur ? cur.p1 : nxt.p1;
-    const int64_t p = q0 + int64_t(in_cur ? rel : rel - cur.nch) * kChunk + lane;
-    pvalid = lane < kChunk && p < q1 && (in_cur || rel - cur.nch < uint32_t(nxt.nch));
-    pcol = pvalid ? __ldg(prm.col + p) : 0;
-    pval = (pvalid && tid < kChunk) ? __ldg(prm.val + p) : 0.0;
-  };
-  auto issue_one = [&]() {
-    const uint32_t st = issued % kStages;
-    if (issued >= kStages) mbar_wait(&empty[st], ((issued / kStages) & 1u) ^ 1u);
-    if (tid < kChunk) {
-      const double wa = pvalid ? prm.alpha * pval : 0.0;        // WALSEngine.cpp:282  alpha * r
-      const double wb = pvalid ? 1.0 + prm.alpha * pval : 0.0;  // WALSEngine.cpp:280  1 + alpha * r
-      wts[st * 2 * kChunk + lane] = wa;
-      wts[st * 2 * kChunk + kChunk + lane] = wb;
-      if (issued - base < uint32_t(cur.nch)) csum_cur += wb; else csum_nxt += wb;
-      mbar_arrive(&full[st]);
-    }
-    const int rsub = tid / TPR, piece = tid % TPR;
-#pragma unroll
-    for (int m = 0; m < kChunk / 4; ++m) {
-      const int row = 4 * m + rsub;
-      const int32_t c = __shfl_sync(0xffffffffu, pcol, row);
-      cp_async16(stagebuf + (size_t(st) * kChunk + row) * SM::LD + piece * 2, prm.Y + int64_t(c) * prm.ldy + piece * 2);
-    }
-    cp_async_arrive(&full[st]);
-    ++issued;
-    prefetch_idx();
-  };
-  prefetch_idx();
-  __syncthreads();  // barriers initialised
+  __syncthreads();  // barriers initialised, first row slot visible
 
   const int fo = (lane & 3) * 8 + (lane >> 2);  // fragment offset inside a tile (see tile_mma_tn)
-  while (cur.row >= 0) {
-    Row nn = fetch(it + 2);  // the row after next: its index loads fly during this row
-    // ---- build ------------------------------------------------------------------------------------
-    double acc[NT + 1][2];
-#pragma unroll
-    for (int t = 0; t <= NT; ++t) {  // accumulators start from the Gram tiles
-      int I, J;
-      acc_tile<NT>(warp, t, I, J);
-      const double2 g = *reinterpret_cast<const double2*>(prm.gram + size_t(SM::gidx(I, J)) * 64 + lane * 2);
-      acc[t][0] = g.x;
-      acc[t][1] = g.y;
+  for (;;) {
+    const volatile RowSlot* cs = slots + (it & 1);
+    if (cs->row < 0) break;
+    // thread 0 walks the next row's index chain (order -> row_ptr) at leisure during this row
+    int nrow = -1;
+    if (tid == 0) {
+      const int sn = slot_of(it + 1);
+      if (sn < prm.nrows) nrow = __ldg(prm.order + sn);
     }
-    double bacc = 0.0;
-    const int bi = tid % SM::KP, bh = tid / SM::KP;
-    const uint32_t lim = base + uint32_t(cur.nch);  // the ring is reused as tile storage: no cross-row prefetch
-    for (int c = 0; c < cur.nch; ++c) {
-      const uint32_t gc = base + c;
-      while (issued < lim && issued < gc + kStages) issue_one();
-      const uint32_t st = gc % kStages;
-      mbar_wait(&full[st], (gc / kStages) & 1u);
-      const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
-      const double* w8 = wts + st * 2 * kChunk;
-      chunk_mma_dispatch<NT, 0>(warp, acc, sb, w8, lane);
-#pragma unroll
-      for (int s = 0; s < kChunk / 2; ++s) bacc += w8[kChunk + 2 * s + bh] * sb[(2 * s + bh) * SM::LD + bi];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);
-    }
-    __syncthreads();  // every warp is done reading the ring before the tiles overwrite it
-    // ---- tiles to shared memory: A(i,i) += lambda (WALSEngine.cpp:290-292), unit pivot on padding -----
-    {
-      const int r = lane >> 2, c0 = 2 * (lane & 3);
-#pragma unroll
-      for (int t = 0; t <= NT; ++t) {
-        int I, J;
-        acc_tile<NT>(warp, t, I, J);
-        double v0 = acc[t][0], v1 = acc[t][1];
-        if (I == J) {
-          const int gi = 8 * I + r;
-          if (c0 == r) v0 = gi < prm.k ? v0 + prm.lambda : 1.0;
-          if (c0 + 1 == r) v1 = gi < prm.k ? v1 + prm.lambda : 1.0;
-        }
-        *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(I, J)) * 64 + lane * 2) = make_double2(v0, v1);
-      }
-      bhalf[tid] = bacc;
+    const double csum = build_row<NT>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k,
+                                      cs->p0, cs->p1, cs->base);
+    int64_t np0 = 0, np1 = 0;
+    if (tid == 0 && nrow >= 0) {
+      np0 = __ldg(prm.row_ptr + nrow);
+      np1 = __ldg(prm.row_ptr + nrow + 1);
     }
     __syncthreads();
     // b = sum of the two half sums; b column tiles (column 0 = b, other columns 0); keep a copy
@@ -597,23 +648,24 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
         const double x = xvec[i];
         part += z * z - prm.lambda * x * x - 2.0 * x * bcopy[i];
       }
-      part += csum_cur;
+      part += csum;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == 0) prm.row_loss[cur.row] = part;
+      if (lane == 0) prm.row_loss[cs->row] = part;
     } else if (warp == 1 || SM::NWARPS == 1) {
-      double* xr = prm.X + (prm.row_offset + cur.row) * prm.ldx;
+      double* xr = prm.X + (prm.row_offset + cs->row) * prm.ldx;
       for (int i = lane; i < SM::KP; i += 32) xr[i] = i < prm.k ? xvec[i] : 0.0;
     }
     // ---- next row -----------------------------------------------------------------------------------
-    base += uint32_t(cur.nch);
-    csum_cur = csum_nxt;
-    csum_nxt = 0.0;
-    cur = nxt;
-    nxt = nn;
+    if (tid == 0) {
+      volatile RowSlot* ns = slots + ((it + 1) & 1);
+      ns->row = nrow;
+      ns->p0 = np0;
+      ns->p1 = np1;
+      ns->base = cs->base + uint32_t((cs->p1 - cs->p0 + kChunk - 1) / kChunk);
+    }
     ++it;
-    prefetch_idx();   // the registers for chunk `issued` were computed in the previous row's frame
-    __syncthreads();  // tiles / xvec / bcopy free again
+    __syncthreads();  // tiles / xvec / bcopy free again, next row slot visible
   }
 }
 
