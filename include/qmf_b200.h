@@ -103,6 +103,63 @@ int64_t qmfb_wals_launch_count(qmfb_wals_t* h);
  * and row-solve kernels */
 int qmfb_wals_last_timing(qmfb_wals_t* h, float* gram_ms, float* solve_ms);
 
+/* ---------------------------------------------------------------- BPR engine (host) -------- */
+typedef struct qmfb_bpr qmfb_bpr_t;
+/* Factors (and optional item biases, BPRConfig::useBiases) resident on `device`, zero-initialised. */
+int qmfb_bpr_create(int device, int64_t nusers, int64_t nitems, int nfactors, int use_biases, qmfb_bpr_t** out);
+int qmfb_bpr_destroy(qmfb_bpr_t* h);
+/* The positive pairs in data_ order (first-appearance dense idx, qmf/bpr/BPREngine.cpp:65-77).
+ * The per-user sorted positive sets used to reject sampled negatives (itemMap_, :79-82) are
+ * derived here. */
+int qmfb_bpr_set_data(qmfb_bpr_t* h, const int32_t* user_idx, const int32_t* item_idx, int64_t npairs);
+/* host row-major n x nfactors (qmf::Matrix layout) <-> device; side = QMFB_SIDE_USER / ITEM */
+int qmfb_bpr_set_factors(qmfb_bpr_t* h, int side, const double* host);
+int qmfb_bpr_get_factors(qmfb_bpr_t* h, int side, double* host);
+int qmfb_bpr_set_biases(qmfb_bpr_t* h, const double* host);
+int qmfb_bpr_get_biases(qmfb_bpr_t* h, double* host);
+/* One Hogwild SGD pass over all pairs, num_neg sampled negatives each (the SGD half of one
+ * iteration of BPREngine::optimize, qmf/bpr/BPREngine.cpp:151-164 -> iterate/iterateBlock ->
+ * sampleRandomNegative -> update :178-220).  Negatives come from Philox4x32-10 keyed by
+ * (seed, epoch); `shuffle` != 0 visits the pairs in a per-epoch pseudo-random order
+ * (BPREngine::shuffle, :276-278).  *n_updates receives npairs * num_neg.  Returns
+ * QMFB_ERR_NOT_FINITE if a gradient was not finite (CHECK at :184-185). */
+int qmfb_bpr_epoch(qmfb_bpr_t* h, double lr, double user_lambda, double item_lambda, double bias_lambda, int num_neg,
+                   uint64_t seed, uint64_t epoch, int shuffle, int64_t* n_updates);
+/* Apply explicit triplets one after the other in the given order (BPREngine::update, :178-220);
+ * the sequential semantics of num_hogwild_threads <= 1, used for exact parity checks. */
+int qmfb_bpr_update_triplets(qmfb_bpr_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t n, double lr,
+                             double user_lambda, double item_lambda, double bias_lambda);
+/* sum over the first n triplets of log(1 + exp(-x)) (loss half of BPREngine::evaluate,
+ * :246-261; the caller applies the reference's tail-drop by passing
+ * n = nthreads * floor(size / nthreads) and divides by size). */
+int qmfb_bpr_eval_loss(qmfb_bpr_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t n, double* sum_out);
+/* device time (ms, CUDA events on the handle's stream) of the last qmfb_bpr_epoch kernel */
+int qmfb_bpr_last_epoch_ms(qmfb_bpr_t* h, float* ms);
+double* qmfb_bpr_factors_device(qmfb_bpr_t* h, int side);
+double* qmfb_bpr_biases_device(qmfb_bpr_t* h);
+int64_t qmfb_bpr_launch_count(qmfb_bpr_t* h);
+
+/* ---------------------------------------------------------------- ranking evaluation ------- */
+/* All-item scoring of nT test users fused with the rank statistics of AUC / AP / P@k / R@k
+ * (replaces Engine::computeTestScores, qmf/Engine.cpp:73-96, and the sorts in
+ * qmf/metrics/Metrics.cpp:65-164).  Host pointers.  U is nusers x k, V is nitems x k row-major,
+ * biases may be NULL.  label_ptr (nT+1) / label_items: per test user the ascending, distinct item
+ * idx whose test label is > 0 (Engine::initAvgTestData, Engine.cpp:58-69).
+ * Outputs, per test user t with nP = label_ptr[t+1]-label_ptr[t] positives:
+ *   cnt[label_ptr[t] + t + i], i = 0..nP : number of NEGATIVE items x such that exactly i
+ *       positives score strictly less than x (scores are bit-identical to the reference's);
+ *   pos_scores[label_ptr[t] + i]        : the positives' scores in ascending order.
+ * A negative in bucket i is preceded, in the reference's order (score descending, positives
+ * first on ties), by exactly nP - i positives; every metric follows from that. */
+int qmfb_eval_rank(int device, const double* U, int64_t nusers, const double* V, int64_t nitems, int k,
+                   const double* biases, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
+                   const int32_t* label_items, int32_t* cnt, double* pos_scores);
+/* same on device pointers (row strides ldu / ldv), asynchronous on `stream`; cnt must hold
+ * label_ptr[nT] + nT ints, error is one int (bit 2 set: too many positives for one user) */
+int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double* V, int64_t ldv, int64_t nitems, int k,
+                       const double* biases, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
+                       const int32_t* label_items, int64_t nlabels, int32_t* cnt, double* pos_scores, int32_t* error);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ _LAZY = {
     "WalsEngineHandle": ("qmf_b200.wals", "WalsEngineHandle"),
     "csr_from_coo": ("qmf_b200.wals", "csr_from_coo"),
     "ShardedWals": ("qmf_b200.wals_dist", "ShardedWals"),
+    "BprEngineHandle": ("qmf_b200.bpr", "BprEngineHandle"),
 }
 
 
@@ -19,7 +20,7 @@ def __getattr__(name):
         import importlib
         mod, attr = _LAZY[name]
         return getattr(importlib.import_module(mod), attr)
-    if name in ("capi", "wals", "wals_dist", "datagen"):
+    if name in ("capi", "wals", "wals_dist", "datagen", "bpr", "evalrank"):
         import importlib
         return importlib.import_module("qmf_b200." + name)
     raise AttributeError(name)

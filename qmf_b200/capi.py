@@ -58,6 +58,25 @@ _SIG = {
     "qmfb_wals_stream": (vp, [vp]),
     "qmfb_wals_launch_count": (c_i64, [vp]),
     "qmfb_wals_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "qmfb_bpr_create": (C.c_int, [C.c_int, c_i64, c_i64, C.c_int, C.c_int, C.POINTER(vp)]),
+    "qmfb_bpr_destroy": (C.c_int, [vp]),
+    "qmfb_bpr_set_data": (C.c_int, [vp, p_i32, p_i32, c_i64]),
+    "qmfb_bpr_set_factors": (C.c_int, [vp, C.c_int, p_f64]),
+    "qmfb_bpr_get_factors": (C.c_int, [vp, C.c_int, p_f64]),
+    "qmfb_bpr_set_biases": (C.c_int, [vp, p_f64]),
+    "qmfb_bpr_get_biases": (C.c_int, [vp, p_f64]),
+    "qmfb_bpr_epoch": (C.c_int, [vp, c_f64, c_f64, c_f64, c_f64, C.c_int, C.c_uint64, C.c_uint64, C.c_int,
+                                 C.POINTER(c_i64)]),
+    "qmfb_bpr_update_triplets": (C.c_int, [vp, p_i32, p_i32, p_i32, c_i64, c_f64, c_f64, c_f64, c_f64]),
+    "qmfb_bpr_eval_loss": (C.c_int, [vp, p_i32, p_i32, p_i32, c_i64, C.POINTER(c_f64)]),
+    "qmfb_bpr_last_epoch_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "qmfb_bpr_factors_device": (vp, [vp, C.c_int]),
+    "qmfb_bpr_biases_device": (vp, [vp]),
+    "qmfb_bpr_launch_count": (c_i64, [vp]),
+    "qmfb_eval_rank": (C.c_int, [C.c_int, p_f64, c_i64, p_f64, c_i64, C.c_int, vp, p_i32, c_i64, p_i64, p_i32, p_i32,
+                                 p_f64]),
+    "qmfb_eval_rank_dev": (C.c_int, [vp, vp, c_i64, vp, c_i64, c_i64, C.c_int, vp, vp, c_i64, vp, vp, c_i64, vp, vp,
+                                     vp]),
 }
 
 EXPORTS = tuple(_SIG)
