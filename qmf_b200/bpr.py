@@ -9,6 +9,7 @@ from .capi import SIDE_ITEM, SIDE_USER, check, lib
 class BprEngineHandle:
     def __init__(self, nusers, nitems, nfactors, use_biases=False, device=0):
         self.nusers, self.nitems, self.k, self.use_biases = int(nusers), int(nitems), int(nfactors), bool(use_biases)
+        self._h = None
         h = C.c_void_p()
         check(lib.qmfb_bpr_create(device, self.nusers, self.nitems, self.k, int(self.use_biases), C.byref(h)))
         self._h = h

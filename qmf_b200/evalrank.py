@@ -66,3 +66,22 @@ def user_metrics(cnt_t, nitems, names):
         else:
             raise ValueError(name)
     return out
+
+
+def average_metric(values, nthreads):
+    """Metric::compute(labels, scores, parallel) (Metrics.cpp:38-52): strided per-thread partial sums
+    folded in thread order (ParallelExecutor::mapReduce), divided by the number of users;
+    nthreads == 0 is the serial overload (:27-36)."""
+    n = len(values)
+    if nthreads <= 0:
+        s = 0.0
+        for v in values:
+            s += v
+        return s / n
+    total = 0.0
+    for th in range(nthreads):
+        part = 0.0
+        for t in range(th, n, nthreads):
+            part = part + values[t]
+        total = total + part
+    return total / n

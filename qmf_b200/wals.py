@@ -35,6 +35,7 @@ class WalsEngineHandle:
 
     def __init__(self, nusers, nitems, nfactors, device=0):
         self.nusers, self.nitems, self.k = int(nusers), int(nitems), int(nfactors)
+        self._h = None
         h = C.c_void_p()
         check(lib.qmfb_wals_create(device, self.nusers, self.nitems, self.k, C.byref(h)))
         self._h = h

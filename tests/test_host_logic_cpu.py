@@ -1,0 +1,147 @@
+"""CPU tests of the host-side logic around the kernels: CSR construction, the metric arithmetic
+that consumes the GPU's rank statistics, shard balancing, and the 2-rank exchange logic of the
+sharded WALS driver (gloo, with the CPU oracle standing in for the CUDA kernels)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from util import init_factors, rel_err, uniform_dataset
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_csr_from_coo_matches_reference_fixture():
+    from qmf_b200.wals import csr_from_coo
+    g = np.load(os.path.join(GOLD, "wals_k30.npz"))
+    for side, (r, c) in enumerate(((g["u"], g["i"]), (g["i"], g["u"]))):
+        ids, rp, ci, va = csr_from_coo(r, c, g["v"])
+        assert np.array_equal(ids, g["rid%d" % side]) and np.array_equal(rp, g["rp%d" % side])
+        assert np.array_equal(ci, g["ci%d" % side])
+        for row in range(len(ids)):   # duplicates may be permuted by the reference's unstable sort
+            sl = slice(rp[row], rp[row + 1])
+            assert sorted(zip(ci[sl], va[sl])) == sorted(zip(g["ci%d" % side][sl], g["va%d" % side][sl]))
+
+
+def _cnt_cpu(labels, scores):
+    pos = np.sort(scores[labels > 0])
+    neg = scores[labels <= 0]
+    idx = np.searchsorted(pos, neg, side="left")       # positives strictly below each negative
+    return np.bincount(idx, minlength=len(pos) + 1).astype(np.int32)
+
+
+def test_metric_arithmetic_from_rank_statistics(oracle_lib):
+    from qmf_b200.evalrank import user_metrics
+    rng = np.random.default_rng(5)
+    names = ["auc", "ap", "p@1", "p@7", "r@7", "r@20"]
+    for trial in range(60):
+        n = int(rng.integers(25, 200))
+        labels = (rng.uniform(size=n) < rng.uniform(0.02, 0.5)).astype(float)
+        labels[rng.integers(0, n)] = 1.0
+        scores = np.round(rng.normal(size=n), 1 if trial % 2 else 6)
+        got = user_metrics(_cnt_cpu(labels, scores), n, names)
+        for name in names:
+            kind, k = oracle.metric_kind(name)
+            assert got[name] == oracle_lib.qmfo_metric_one(kind, k, labels, scores, n), (trial, name)
+    # AUC degenerate classes return 1.0 (Metrics.cpp:80-83)
+    assert user_metrics(np.array([5], np.int32), 5, ["auc"])["auc"] == 1.0
+    assert user_metrics(np.zeros(4, np.int32), 3, ["auc"])["auc"] == 1.0
+
+
+def test_balanced_row_ranges():
+    from qmf_b200.wals_dist import balanced_row_ranges
+    rng = np.random.default_rng(1)
+    lens = rng.zipf(1.5, size=5000).clip(1, 4000)
+    rp = np.zeros(5001, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    for world in (1, 2, 3, 8):
+        rr = balanced_row_ranges(rp, world)
+        assert rr[0][0] == 0 and rr[-1][1] == 5000 and all(a[1] == b[0] for a, b in zip(rr, rr[1:]))
+        nnz = [rp[e] - rp[b] for b, e in rr]
+        assert max(nnz) <= rp[-1] / world + lens.max()
+
+
+class OracleKernels:
+    """CPU stand-in for the CUDA kernels (dense k x k Gram as the 'packed' form) — exercises only
+    the sharding / exchange logic of ShardedWals."""
+    launches_per_half_step = 4
+
+    def __init__(self):
+        self.O = oracle.oracle()
+
+    def padded_k(self, k):
+        return k
+
+    def gram_packed_len(self, k):
+        return k * k
+
+    def gram_workspace_len(self, k):
+        return 1
+
+    def gram(self, Y, rb, re, k, ws, out):
+        G = np.zeros((k, k))
+        if re > rb:
+            self.O.qmfo_gram(np.ascontiguousarray(Y[rb:re].numpy()), re - rb, k, G)
+        out.copy_(torch.from_numpy(G.reshape(-1)))
+
+    def solve(self, X, row_offset, Y, k, row_ptr, col, val, order, gram, alpha, lam, row_loss, loss_sum, scratch):
+        G = np.ascontiguousarray(gram.numpy().reshape(k, k))
+        Yn = np.ascontiguousarray(Y.numpy())
+        rp, c, v = row_ptr.numpy(), col.numpy(), val.numpy()
+        total = 0.0
+        x = np.zeros(k)
+        for r in range(len(rp) - 1):
+            sl = slice(rp[r], rp[r + 1])
+            total += self.O.qmfo_wals_update_row(Yn, k, np.ascontiguousarray(c[sl]), np.ascontiguousarray(v[sl]),
+                                                 rp[r + 1] - rp[r], G, alpha, lam, x)
+            X[row_offset + r] = torch.from_numpy(x.copy())
+        loss_sum[0] = total
+
+
+def _problem():
+    from qmf_b200.wals import csr_from_coo
+    u, i, v = uniform_dataset(90, 60, 1500, 8, id_scale=(2, 5))
+    uids, urp, uci, uv = csr_from_coo(u, i, v)
+    iids, irp, ici, iv = csr_from_coo(i, u, v)
+    return (len(uids), len(iids), 12, (urp, uci, uv), (irp, ici, iv), init_factors(len(iids), 12, 2))
+
+
+def _rank_main(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from qmf_b200.wals_dist import ShardedWals
+    NU, NI, k, ucsr, icsr, Y0 = _problem()
+    t = lambda a: tuple(torch.from_numpy(np.ascontiguousarray(x)) for x in a)
+    sw = ShardedWals(NU, NI, k, t(ucsr), t(icsr), torch.device("cpu"), rank, world, kernels=OracleKernels())
+    sw.set_factors(1, Y0)
+    losses = [float(sw.epoch(40.0, 0.05)) for _ in range(2)]
+    if rank == 0:
+        np.savez(out_path, X=sw.get_factors(0).numpy(), Y=sw.get_factors(1).numpy(), losses=np.array(losses),
+                 ranges=np.array(sw.ranges[0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_wals_two_ranks_gloo(tmp_path, oracle_lib):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_rank_main, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    assert 0 < got["ranges"][0][1] < 90                # really split in two shards
+    NU, NI, k, ucsr, icsr, Y0 = _problem()
+    X, Y = np.zeros((NU, k)), Y0.copy()
+    losses = []
+    for _ in range(2):
+        oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, *ucsr, 40.0, 0.05, NU, NI, 1)
+        losses.append(oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, *icsr, 40.0, 0.05, NU, NI, 1))
+    # the 2-rank Gram is the sum of two partial Grams (different association): ~1e-16 relative
+    assert rel_err(got["X"], X) < 1e-11 and rel_err(got["Y"], Y) < 1e-11
+    assert np.allclose(got["losses"], losses, rtol=1e-12, atol=0)
