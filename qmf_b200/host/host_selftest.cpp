@@ -1,0 +1,121 @@
+// CPU self-test of the host-side mirror (no GPU): the known-answer vectors of the reference's
+// gtests for the classes whose surface is mirrored here.  Exit code 0 = all good.
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <sstream>
+
+#include <qmf/DatasetReader.h>
+#include <qmf/Engine.h>
+#include <qmf/Matrix.h>
+#include <qmf/metrics/Metrics.h>
+#include <qmf/utils/Util.h>
+
+static int failures = 0;
+#define EXPECT(cond)                                                      \
+  do {                                                                    \
+    if (!(cond)) {                                                        \
+      std::fprintf(stderr, "FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond); \
+      ++failures;                                                         \
+    }                                                                     \
+  } while (0)
+
+using qmf::Double;
+
+static Double metric(const char* name, std::vector<Double> labels, std::vector<Double> scores) {
+  qmf::MetricSpec spec;
+  EXPECT(qmf::MetricsManager::get().lookup(name, spec));
+  return qmf::computeMetric(spec, labels, scores);
+}
+
+int main() {
+  // qmf/test/MetricsTest.cpp:35-88
+  EXPECT(metric("mse", {1, 0}, {0.5, 0.5}) == 0.25);
+  EXPECT(metric("auc", {1, 0}, {3, 2}) == 1.0);
+  EXPECT(metric("auc", {0, 1}, {3, 2}) == 0.0);
+  EXPECT(metric("auc", {1, 1, 0}, {3, 2, 0}) == 1.0);
+  EXPECT(metric("auc", {1, 0, 1}, {3, 2, 0}) == 0.5);
+  EXPECT(metric("auc", {0, 1, 1}, {3, 2, 0}) == 0.0);
+  EXPECT(metric("p@1", {1, 1}, {3, 2}) == 1.0);
+  EXPECT(metric("p@2", {0, 1, 0}, {3, 2, 1}) == 0.5);
+  EXPECT(metric("p@2", {0, 1, 0}, {3, 1, 2}) == 0.0);
+  EXPECT(metric("r@1", {1, 1}, {3, 2}) == 0.5);
+  EXPECT(metric("r@2", {0, 1, 0}, {3, 2, 1}) == 1.0);
+  EXPECT(metric("r@2", {0, 1, 0}, {3, 1, 2}) == 0.0);
+  EXPECT(metric("ap", {0, 1}, {3, 2}) == 0.5);
+  EXPECT(metric("ap", {0, 1, 0}, {3, 1, 2}) == 1.0 / 3);
+  // qmf/test/MetricsManagerTest.cpp
+  std::string base;
+  size_t k = 0;
+  EXPECT(qmf::detail::parseAtKMetric("p@5", base, k) && base == "p" && k == 5);
+  EXPECT(!qmf::detail::parseAtKMetric("auc", base, k) && !qmf::detail::parseAtKMetric("@5", base, k));
+  EXPECT(qmf::MetricsManager::get().exists("r@10") && !qmf::MetricsManager::get().exists("foo") &&
+         !qmf::MetricsManager::get().exists("x@3"));
+  // qmf/test/EngineTest.cpp:113-139 (exact output text)
+  {
+    qmf::IdIndex index;
+    index.getOrSetIdx(3);
+    index.getOrSetIdx(5);
+    qmf::FactorData f(2, 3);
+    f.setFactors([](size_t i, size_t j) { return Double(i * 3 + j); });
+    std::ostringstream out;
+    qmf::Engine::saveFactors(f, index, out);
+    EXPECT(out.str() == "3 0.000000000 1.000000000 2.000000000\n5 3.000000000 4.000000000 5.000000000\n");
+    qmf::FactorData fb(2, 3, true);
+    fb.setFactors([](size_t i, size_t j) { return Double(i * 3 + j); });
+    fb.setBiases([](size_t i) { return Double(5 + i); });
+    std::ostringstream outb;
+    qmf::Engine::saveFactors(fb, index, outb);
+    EXPECT(outb.str() == "3 5.000000000 0.000000000 1.000000000 2.000000000\n5 6.000000000 3.000000000 4.000000000 5.000000000\n");
+  }
+  // qmf/test/EngineTest.cpp:23-73 (which users / labels are evaluated)
+  {
+    qmf::IdIndex users, items;
+    for (int64_t u : {1, 2, 3}) users.getOrSetIdx(u);
+    for (int64_t i : {10, 20, 30, 40}) items.getOrSetIdx(i);
+    std::vector<qmf::DatasetElem> test = {{1, 20, 1.0}, {1, 99, 1.0}, {7, 10, 1.0}, {3, 40, 2.0}, {3, 10, 0.0}, {3, 40, 3.0}};
+    qmf::Engine::TestData td;
+    qmf::Engine::initAvgTestData(td, test, users, items);
+    EXPECT(td.users.size() == 2 && td.labelPtr.size() == 3);
+    for (size_t t = 0; t < td.users.size(); ++t) {
+      const size_t n = size_t(td.labelPtr[t + 1] - td.labelPtr[t]);
+      if (td.users[t] == 0) EXPECT(n == 1 && td.labelItems[size_t(td.labelPtr[t])] == 1);
+      if (td.users[t] == 2) EXPECT(n == 1 && td.labelItems[size_t(td.labelPtr[t])] == 3);
+    }
+  }
+  // qmf/test/MatrixTest.cpp:92-116: symmetric INDEFINITE 50 x 50, residual <= 1e-8
+  {
+    const size_t n = 50;
+    qmf::Matrix A(n, n);
+    qmf::Vector b(n);
+    unsigned s = 12345;
+    auto rnd = [&s]() { s = s * 1664525u + 1013904223u; return (s >> 8) / double(1 << 24) - 0.5; };
+    for (size_t i = 0; i < n; ++i) {
+      b(i) = rnd();
+      for (size_t j = i; j < n; ++j) A(i, j) = A(j, i) = rnd();
+    }
+    qmf::Vector x = qmf::linearSymmetricSolve(A, b);
+    double worst = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+      double r = -b(i);
+      for (size_t j = 0; j < n; ++j) r += A(i, j) * x(j);
+      worst = std::fmax(worst, std::fabs(r));
+    }
+    EXPECT(worst <= 1e-8);
+    qmf::Matrix T = A.transpose();
+    EXPECT(T(3, 7) == A(7, 3) && (A + T)(2, 9) == 2 * A(2, 9));
+  }
+  // qmf/test/DatasetReaderTest.cpp:25-58, UtilTest.cpp
+  {
+    auto in = std::make_unique<std::istringstream>("1 2 3\n-4 5 0.5\n");
+    qmf::DatasetReader reader(std::move(in));
+    const auto d = reader.readAll();
+    EXPECT(d.size() == 2 && d[0].userId == 1 && d[0].itemId == 2 && d[0].value == 3.0 && d[1].userId == -4 && d[1].value == 0.5);
+    const auto parts = qmf::split("auc,,p@10,", ',');
+    EXPECT(parts.size() == 2 && parts[0] == "auc" && parts[1] == "p@10");
+  }
+  // averaging order of Metric::compute(labels, scores, parallel)
+  EXPECT(qmf::averageOverUsers({1.0, 2.0, 3.0, 4.0, 5.0}, 2) == ((1.0 + 3.0 + 5.0) + (2.0 + 4.0)) / 5);
+  if (failures == 0) std::printf("host selftest ok\n");
+  return failures == 0 ? 0 : 1;
+}

@@ -1,0 +1,57 @@
+// Engine base class with the reference's virtual surface (qmf/Engine.h:32-64) and the shared
+// evaluation / output helpers.  Evaluation data is kept as a CSR of positive test items per test
+// user (the reference materialises dense nT x nitems label and score matrices, Engine.cpp:52-69;
+// the GPU path never needs them).
+#pragma once
+#include <memory>
+#include <ostream>
+#include <string>
+#include <vector>
+
+#include <qmf/DatasetReader.h>
+#include <qmf/FactorData.h>
+#include <qmf/metrics/Metrics.h>
+#include <qmf/utils/IdIndex.h>
+
+namespace qmf {
+
+class Engine {
+ public:
+  Engine() = default;
+  virtual ~Engine() = default;
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+
+  virtual void init(const std::vector<DatasetElem>& /*dataset*/) {}
+  virtual void initTest(const std::vector<DatasetElem>& /*testDataset*/) {}
+  virtual void optimize() {}
+  virtual void evaluate(const size_t /*epoch*/) {}
+  virtual void saveUserFactors(const std::string& /*fileName*/) const {}
+  virtual void saveItemFactors(const std::string& /*fileName*/) const {}
+
+  struct TestData {
+    std::vector<size_t> users;        // test user idx, in the reference's order
+    std::vector<int64_t> labelPtr;    // users.size() + 1
+    std::vector<int32_t> labelItems;  // ascending item idx with test label > 0
+    bool empty() const { return users.empty(); }
+  };
+
+  // Which users are evaluated and in what order: identical to Engine::initAvgTestData
+  // (qmf/Engine.cpp:27-71) - users with >= 1 test line whose user AND item are known from
+  // training, iterated in std::unordered_set order, optionally std::shuffle'd with mt19937(seed)
+  // and truncated to numTestUsers.  A label is the value of the LAST test line of (user, item).
+  static void initAvgTestData(TestData& out, const std::vector<DatasetElem>& testDataset, const IdIndex& userIndex,
+                              const IdIndex& itemIndex, size_t numTestUsers = 0, int32_t seed = 0);
+
+  // scores of every item for every test user + rank statistics on the GPU (qmfb_eval_rank), then
+  // every requested test-average metric recorded with the reference's averaging order
+  static void computeAndRecordTestAvgMetrics(MetricsEngine& metrics, size_t epoch, const TestData& test,
+                                             const FactorData& userFactors, const FactorData& itemFactors,
+                                             size_t nthreads, int device);
+
+  // "<id>[ <bias>] <f0> ... <fk-1>\n", fixed, 9 decimals (qmf/Engine.cpp:98-122)
+  static void saveFactors(const FactorData& factorData, const IdIndex& index, const std::string& fileName);
+  static void saveFactors(const FactorData& factorData, const IdIndex& index, std::ostream& out);
+};
+
+}  // namespace qmf

@@ -1,0 +1,148 @@
+#include <qmf/wals/WALSEngine.h>
+
+#include <algorithm>
+#include <random>
+
+#include "qmf_b200.h"
+
+namespace qmf {
+
+namespace {
+
+#define QMFB_OK_OR_DIE(call)                                        \
+  do {                                                              \
+    const int qmfb_rc_ = (call);                                    \
+    CHECK_EQ(qmfb_rc_, 0) << #call << ": " << qmfb_last_error();    \
+  } while (0)
+
+struct Cell {
+  int64_t row, col;
+  Double value;
+};
+
+// sort by (row id, col id) and cut into rows; the dense index of a row is its rank
+void buildCsr(std::vector<Cell>& cells, IdIndex& rowIndex, WALSEngine::Csr& csr) {
+  std::sort(cells.begin(), cells.end(), [](const Cell& a, const Cell& b) {
+    return a.row != b.row ? a.row < b.row : a.col < b.col;
+  });
+  csr.rowPtr.assign(1, 0);
+  for (size_t p = 0; p < cells.size(); ++p) {
+    if (p == 0 || cells[p].row != cells[p - 1].row) {
+      if (p != 0) csr.rowPtr.push_back(int64_t(p));
+      const size_t idx = rowIndex.getOrSetIdx(cells[p].row);
+      CHECK_EQ(idx + 1, csr.rowPtr.size());
+    }
+  }
+  if (!cells.empty()) csr.rowPtr.push_back(int64_t(cells.size()));
+}
+
+void fillCols(const std::vector<Cell>& cells, const IdIndex& colIndex, WALSEngine::Csr& csr) {
+  csr.col.resize(cells.size());
+  csr.val.resize(cells.size());
+  for (size_t p = 0; p < cells.size(); ++p) {
+    csr.col[p] = int32_t(colIndex.idx(cells[p].col));
+    csr.val[p] = cells[p].value;
+  }
+}
+
+}  // namespace
+
+WALSEngine::WALSEngine(const WALSConfig& config, const std::unique_ptr<MetricsEngine>& metricsEngine, const size_t nthreads)
+  : config_(config), metricsEngine_(metricsEngine), nthreads_(nthreads) {
+  if (metricsEngine_ && !metricsEngine_->testAvgMetrics().empty() && metricsEngine_->config().numTestUsers == 0) {
+    LOG(WARNING) << "computing average test metrics on all users can be slow! "
+                    "Set numTestUsers > 0 to sample some of them";
+  }
+}
+
+WALSEngine::~WALSEngine() {
+  if (dev_ != nullptr) qmfb_wals_destroy(dev_);
+}
+
+void WALSEngine::init(const std::vector<DatasetElem>& dataset) {
+  CHECK(!userFactors_ && !itemFactors_) << "engine was already initialized with train data";
+  CHECK(!dataset.empty()) << "empty training dataset";
+  std::vector<Cell> byUser(dataset.size()), byItem(dataset.size());
+  for (size_t p = 0; p < dataset.size(); ++p) {
+    byUser[p] = Cell{dataset[p].userId, dataset[p].itemId, dataset[p].value};
+    byItem[p] = Cell{dataset[p].itemId, dataset[p].userId, dataset[p].value};
+  }
+  buildCsr(byUser, userIndex_, csr_[0]);
+  buildCsr(byItem, itemIndex_, csr_[1]);
+  fillCols(byUser, itemIndex_, csr_[0]);
+  fillCols(byItem, userIndex_, csr_[1]);
+
+  userFactors_ = std::make_unique<FactorData>(nusers(), config_.nfactors);
+  itemFactors_ = std::make_unique<FactorData>(nitems(), config_.nfactors);
+  if (config_.DistributionFile.empty()) {
+    // user factors need no initial value: the first half-step overwrites them
+    std::mt19937 gen(config_.seed >= 0 ? static_cast<uint32_t>(config_.seed) : std::random_device()());
+    std::uniform_real_distribution<Double> dist(-config_.initDistributionBound, config_.initDistributionBound);
+    itemFactors_->setFactors([&](size_t, size_t) { return dist(gen); });
+  } else {
+    itemFactors_->setFactors(config_.DistributionFile);
+  }
+
+  QMFB_OK_OR_DIE(qmfb_wals_create(config_.device, int64_t(nusers()), int64_t(nitems()), int(config_.nfactors), &dev_));
+  QMFB_OK_OR_DIE(qmfb_wals_set_csr(dev_, QMFB_SIDE_USER, 0, int64_t(nusers()), csr_[0].rowPtr.data(), csr_[0].col.data(),
+                                   csr_[0].val.data()));
+  QMFB_OK_OR_DIE(qmfb_wals_set_csr(dev_, QMFB_SIDE_ITEM, 0, int64_t(nitems()), csr_[1].rowPtr.data(), csr_[1].col.data(),
+                                   csr_[1].val.data()));
+  QMFB_OK_OR_DIE(qmfb_wals_set_factors(dev_, QMFB_SIDE_ITEM, itemFactors_->getFactors().data()));
+}
+
+void WALSEngine::initTest(const std::vector<DatasetElem>& testDataset) {
+  CHECK(test_.empty()) << "engine was already initialized with test data";
+  if (metricsEngine_ && !metricsEngine_->testAvgMetrics().empty()) {
+    initAvgTestData(test_, testDataset, userIndex_, itemIndex_, metricsEngine_->config().numTestUsers,
+                    metricsEngine_->config().seed);
+  }
+}
+
+Double WALSEngine::iterate(int side) {
+  double lossSum = 0.0;
+  QMFB_OK_OR_DIE(qmfb_wals_half_step(dev_, side, config_.confidenceWeight, config_.regularizationLambda, &lossSum));
+  hostStale_ = true;
+  return lossSum / nusers() / nitems();
+}
+
+void WALSEngine::optimize() {
+  CHECK(userFactors_ && itemFactors_) << "no factor data, have you initialized the engine?";
+  for (size_t epoch = 1; epoch <= config_.nepochs; ++epoch) {
+    iterate(QMFB_SIDE_USER);                      // fix item factors, update user factors
+    const Double loss = iterate(QMFB_SIDE_ITEM);  // fix user factors, update item factors
+    LOG(INFO) << "epoch " << epoch << ": train loss = " << loss;
+    evaluate(epoch);
+  }
+  syncFactorsToHost();
+}
+
+void WALSEngine::syncFactorsToHost() const {
+  if (!hostStale_ || dev_ == nullptr) return;
+  QMFB_OK_OR_DIE(qmfb_wals_get_factors(dev_, QMFB_SIDE_USER, userFactors_->getFactors().data()));
+  QMFB_OK_OR_DIE(qmfb_wals_get_factors(dev_, QMFB_SIDE_ITEM, itemFactors_->getFactors().data()));
+  hostStale_ = false;
+}
+
+void WALSEngine::evaluate(const size_t epoch) {
+  if (metricsEngine_ && !metricsEngine_->testAvgMetrics().empty() && !test_.empty() &&
+      (metricsEngine_->config().alwaysCompute || epoch == config_.nepochs)) {
+    LOG(INFO) << "do compute evaluate ...";
+    syncFactorsToHost();
+    computeAndRecordTestAvgMetrics(*metricsEngine_, epoch, test_, *userFactors_, *itemFactors_, nthreads_, config_.device);
+  }
+}
+
+void WALSEngine::saveUserFactors(const std::string& fileName) const {
+  CHECK(userFactors_) << "user factors wasn't initialized";
+  syncFactorsToHost();
+  saveFactors(*userFactors_, userIndex_, fileName);
+}
+
+void WALSEngine::saveItemFactors(const std::string& fileName) const {
+  CHECK(itemFactors_) << "item factors wasn't initialized";
+  syncFactorsToHost();
+  saveFactors(*itemFactors_, itemIndex_, fileName);
+}
+
+}  // namespace qmf

@@ -1,0 +1,71 @@
+// Weighted ALS engine with the reference's public surface (qmf/wals/WALSEngine.h:35-60); the
+// half-step (Gram, per-row normal equations, solve, loss) runs on the GPU through the C ABI.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <qmf/Engine.h>
+
+struct qmfb_wals;
+
+namespace qmf {
+
+struct WALSConfig {
+  size_t nepochs;
+  size_t nfactors;
+  Double regularizationLambda;
+  Double confidenceWeight;
+  Double initDistributionBound;
+  std::string DistributionFile;
+  int64_t seed = -1;   // additive: >= 0 seeds the initial item factors (the reference uses random_device)
+  int device = 0;      // additive: CUDA device ordinal
+};
+
+class WALSEngine : public Engine {
+ public:
+  explicit WALSEngine(const WALSConfig& config, const std::unique_ptr<MetricsEngine>& metricsEngine,
+                      const size_t nthreads = 16);
+  ~WALSEngine() override;
+
+  void init(const std::vector<DatasetElem>& dataset) override;
+  void initTest(const std::vector<DatasetElem>& testDataset) override;
+  void optimize() override;
+  void evaluate(const size_t epoch) override;
+  void saveUserFactors(const std::string& fileName) const override;
+  void saveItemFactors(const std::string& fileName) const override;
+
+  size_t nusers() const { return userIndex_.size(); }
+  size_t nitems() const { return itemIndex_.size(); }
+
+  // CSR of one orientation exactly as WALSEngine::groupSignals builds its signal groups
+  // (qmf/wals/WALSEngine.cpp:130-163): rows in ascending raw id, entries in ascending raw id of
+  // the other side, duplicates kept; col holds the dense idx (== rank) of the other side.
+  struct Csr {
+    std::vector<int64_t> rowPtr;
+    std::vector<int32_t> col;
+    std::vector<Double> val;
+  };
+  const Csr& userCsr() const { return csr_[0]; }
+  const Csr& itemCsr() const { return csr_[1]; }
+  const FactorData& userFactors() const { return *userFactors_; }
+  const FactorData& itemFactors() const { return *itemFactors_; }
+
+ private:
+  // one half-step on the device; returns the loss divided by nusers and nitems (WALSEngine.cpp:215)
+  Double iterate(int side);
+  void syncFactorsToHost() const;
+
+  const WALSConfig& config_;
+  const std::unique_ptr<MetricsEngine>& metricsEngine_;
+  const size_t nthreads_;
+
+  IdIndex userIndex_, itemIndex_;
+  Csr csr_[2];
+  std::unique_ptr<FactorData> userFactors_, itemFactors_;  // host mirrors
+  mutable bool hostStale_ = false;
+  qmfb_wals* dev_ = nullptr;
+  TestData test_;
+};
+
+}  // namespace qmf

@@ -1,0 +1,92 @@
+"""End to end through the drop-in binaries (qmf_b200/host/bin/wals, bpr) on the GPU: same flags,
+same dataset / distribution / factor file formats and log lines as the reference; outputs are
+compared with what the reference's own `wals` binary produced (tests/golden/cli, made by
+make_cli_golden.py)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "tests", "golden", "cli")
+BIN = os.path.join(ROOT, "qmf_b200", "host", "bin")
+
+
+def read_factors(path):
+    ids, rows = [], []
+    for line in open(path):
+        parts = line.split()
+        ids.append(int(parts[0]))
+        rows.append([float(x) for x in parts[1:]])
+        assert all(re.fullmatch(r"-?\d+\.\d{9}", x) for x in parts[1:])      # fixed, 9 decimals
+    return np.array(ids), np.array(rows)
+
+
+def log_values(text):
+    out = {}
+    for m in re.finditer(r"epoch (\d+): train loss = (\S+)", text):
+        out[("loss", int(m.group(1)))] = float(m.group(2).rstrip(","))
+    for m in re.finditer(r"epoch (\d+): recorded metric (\S+) = (\S+)", text):
+        out[(m.group(2), int(m.group(1)))] = float(m.group(3))
+    return out
+
+
+def test_wals_binary_matches_reference_binary(tmp_path):
+    uf, itf = str(tmp_path / "u.txt"), str(tmp_path / "i.txt")
+    cmd = [os.path.join(BIN, "wals"), "--nepochs=3", "--nfactors=30", "--regularization_lambda=0.05", "-confidence_weight=40",
+           "--nthreads", "4", "--train_dataset=" + os.path.join(CLI, "train.txt"), "--test_dataset=" + os.path.join(CLI, "test.txt"),
+           "--distribution_file=" + os.path.join(CLI, "dist.txt"), "--test_avg_metrics=auc,ap,p@10,r@10", "--test_always",
+           "--user_factors=" + uf, "--item_factors=" + itf]
+    r = subprocess.run(cmd, env=dict(os.environ, QMF_LOG_PRECISION="17"), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for mine, ref in ((uf, "ref_user_factors.txt"), (itf, "ref_item_factors.txt")):
+        ids, F = read_factors(mine)
+        rids, RF = read_factors(os.path.join(CLI, ref))
+        assert np.array_equal(ids, rids)                      # ascending raw id order, bit-exact indexing
+        assert np.abs(F - RF).max() <= 2.5e-9                 # the files carry 9 decimals
+    got, want = log_values(r.stderr), log_values(open(os.path.join(CLI, "ref_log.txt")).read())
+    assert set(got) == set(want) and len(want) == 15
+    for key, w in want.items():
+        tol = 1e-12 if key[0] == "loss" else 1e-9
+        assert abs(got[key] - w) <= tol * max(abs(w), 1e-30), (key, got[key], w)
+    for line in ("loading training data", "loading test data", "training", "saving model output"):
+        assert line in r.stderr
+
+
+def test_wals_default_log_format():
+    r = subprocess.run([os.path.join(BIN, "wals"), "--nepochs=1", "--nfactors=8", "--seed=5",
+                        "--train_dataset=" + os.path.join(CLI, "train.txt")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert re.search(r"epoch 1: train loss = \d\.\d{1,6}\n", r.stderr)           # ostream default precision
+    assert "missing model output filenames" in r.stderr
+
+
+def test_bpr_binary_runs_and_learns(tmp_path):
+    # planted preferences written in the reference's dataset format
+    rng = np.random.default_rng(3)
+    nu, ni = 500, 300
+    A, B = rng.normal(size=(nu, 5)), rng.normal(size=(ni, 5))
+    S = A @ B.T
+    top = np.argsort(-S, axis=1)[:, :40]
+    train, test = str(tmp_path / "train.txt"), str(tmp_path / "test.txt")
+    with open(train, "w") as ft, open(test, "w") as fe:
+        for u in range(nu):
+            for n, i in enumerate(rng.permutation(top[u])):
+                (fe if n < 6 else ft).write("%d %d 1\n" % (1000 + u, 5000 + i))
+    uf, itf = str(tmp_path / "u.txt"), str(tmp_path / "i.txt")
+    cmd = [os.path.join(BIN, "bpr"), "--nepochs=12", "--nfactors=16", "--use_biases", "--num_negative_samples=3", "--seed=11",
+           "--train_dataset=" + train, "--test_dataset=" + test, "--test_avg_metrics=auc,p@10", "--num_hogwild_threads=8",
+           "--user_factors=" + uf, "--item_factors=" + itf]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    losses = [(float(a), float(b)) for a, b in re.findall(r"train loss = (\S+), test loss = (\S+)", r.stderr)]
+    assert len(losses) == 12 and losses[-1][0] < 0.45 < losses[0][0] + 0.3 and losses[-1][1] < 0.62
+    auc = float(re.search(r"epoch 12: recorded metric test_avg_auc = (\S+)", r.stderr).group(1))
+    assert auc > 0.8, auc
+    ids, F = read_factors(uf)
+    assert ids[0] == 1000 and F.shape == (nu, 16)             # first-appearance order, no bias column for users
+    iids, G = read_factors(itf)
+    assert G.shape[1] == 17                                   # bias + 16 factors
