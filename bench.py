@@ -205,6 +205,66 @@ def run_reference(args, cfg, workload):
 
 
 # ------------------------------------------------------------------------------------------------
+# BPR (north_star part 2): triplet updates/s on 1 GPU, as achieved algorithmic HBM GB/s
+# ------------------------------------------------------------------------------------------------
+BPR_SHAPES = {
+    # name: (nusers, nitems, npairs, nfactors)
+    "c2": (10_000, 5_000, 450_000, 30),          # BASELINE.json configs[1] (L2-resident: 3.6 MB of factors)
+    "large": (4_000_000, 1_000_000, 40_000_000, 64),   # 2.6 GB of factors: HBM-resident gather/scatter
+}
+
+
+def bpr_pairs(nu, ni, npairs, seed):
+    rng = np.random.default_rng(seed)
+    u = rng.integers(0, nu, size=npairs, dtype=np.int64).astype(np.int32)
+    i = rng.integers(0, ni, size=npairs, dtype=np.int64).astype(np.int32)
+    return u, i
+
+
+def run_bpr_ours(shape, epochs=5, warmup=2, device=0):
+    from qmf_b200.bpr import BprEngineHandle
+    nu, ni, npairs, k = BPR_SHAPES[shape]
+    u, i = bpr_pairs(nu, ni, npairs, 11)
+    h = BprEngineHandle(nu, ni, k, use_biases=True, device=device)
+    h.set_data(u, i)
+    rng = np.random.default_rng(1)
+    h.set_factors(0, rng.uniform(-0.01, 0.01, (nu, k)))
+    h.set_factors(1, rng.uniform(-0.01, 0.01, (ni, k)))
+    h.set_biases(rng.uniform(-0.01, 0.01, ni))
+    lr, ms = 0.05, []
+    for e in range(warmup + epochs):
+        h.epoch(lr, 0.025, 0.0025, 1.0, 3, seed=7, epoch=e, shuffle=True)
+        if e >= warmup:
+            ms.append(h.last_epoch_ms())
+        lr *= 0.9
+    upd = npairs * 3
+    per_triplet = 6 * 8 * k + 32 + 24
+    sec = float(np.mean(ms)) * 1e-3
+    out = {"shape": {"nusers": nu, "nitems": ni, "npairs": npairs, "nfactors": k, "num_neg": 3, "use_biases": True},
+           "updates_per_s": upd / sec, "ms_per_epoch": sec * 1e3, "algorithmic_bytes_per_triplet": per_triplet,
+           "achieved_gbs": upd * per_triplet / sec * 1e-9, "launches_per_epoch": 1}
+    h.close()
+    return out
+
+
+def run_bpr_reference(threads):
+    """the reference's own BPREngine::optimize (Hogwild on all host threads) on the C2 shape"""
+    import oracle
+    if not oracle.ref_available():
+        return None
+    L = oracle.ref()
+    L.ref_set_min_log_level(2)
+    nu, ni, npairs, k = BPR_SHAPES["c2"]
+    u, i = bpr_pairs(nu, ni, npairs, 11)
+    h = L.ref_bpr_create(k, 2, 0.05, 1.0, 0.025, 0.0025, 0.9, 1, 0.01, 3, threads, 1, 3, 42, threads, None, 0, 0, 7)
+    L.ref_bpr_init(h, u.astype(np.int64) + 1, i.astype(np.int64) + 1, np.ones(npairs), npairs)
+    sec = L.ref_bpr_optimize(h)     # 2 epochs incl. the eval-loss passes the reference always runs
+    L.ref_bpr_destroy(h)
+    return {"updates_per_s": 2 * npairs * 3 / sec, "cores": threads, "kind": "reference",
+            "sample": "2 epochs of BPREngine::optimize on the C2 shape, num_hogwild_threads = nthreads = %d" % threads}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, cfg, workload):
@@ -359,6 +419,18 @@ def run_ours(args, cfg, workload):
                         "sample": "%d of %d user rows + %d of %d item rows (+ serial Gram on %d rows) through the "
                                   "reference's updateFactorsForOne, extrapolated by row count" % (su, nu, si, ni, sg)}
 
+    bpr = None
+    if rank == 0 and world == 1 and not args.no_bpr:
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        bpr = {}
+        for shape in ("c2", "large"):
+            r = run_bpr_ours(shape, device=local_rank)
+            r["roofline"] = {"bound": "hbm", "achieved": r["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                             "frac": r["achieved_gbs"] / hbm}
+            bpr[shape] = r
+        if not args.no_cpu_baseline:
+            bpr["cpu_baseline_c2"] = run_bpr_reference(os.cpu_count() or 1)
+
     if rank == 0:
         line = {
             "metric": "wals_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
@@ -368,7 +440,7 @@ def run_ours(args, cfg, workload):
                        "lambda": LAMBDA, "parallelism": "rows x%d" % world,
                        "l2": "inputs (2.9 GB) larger than the 126 MB L2; no flush"},
             "loss": loss_value, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
-            "cpu_baseline": cpu_baseline, "lib": os.path.relpath(capi.LIB_PATH, ROOT),
+            "cpu_baseline": cpu_baseline, "bpr": bpr, "lib": os.path.relpath(capi.LIB_PATH, ROOT),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -384,6 +456,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c1", "c3", "c4"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bpr", action="store_true")
     args = ap.parse_args()
     from qmf_b200.datagen import CONFIGS
     cfg = CONFIGS[args.workload]

@@ -133,6 +133,10 @@ int qmfb_bpr_update_triplets(qmfb_bpr_t* h, const int32_t* u, const int32_t* i, 
  * :246-261; the caller applies the reference's tail-drop by passing
  * n = nthreads * floor(size / nthreads) and divides by size). */
 int qmfb_bpr_eval_loss(qmfb_bpr_t* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t n, double* sum_out);
+/* Upper bound on the number of pairs processed concurrently (the GPU analogue of
+ * --num_hogwild_threads, qmf/bpr.cpp:39): 0 = automatic, min(nusers, nitems) / 2 capped by what
+ * the device can hold; more pairs in flight means staler gradients per row. */
+int qmfb_bpr_set_concurrency(qmfb_bpr_t* h, int64_t max_pairs_in_flight);
 /* device time (ms, CUDA events on the handle's stream) of the last qmfb_bpr_epoch kernel */
 int qmfb_bpr_last_epoch_ms(qmfb_bpr_t* h, float* ms);
 double* qmfb_bpr_factors_device(qmfb_bpr_t* h, int side);

@@ -73,6 +73,9 @@ class BprEngineHandle:
         used = (n // nthreads) * nthreads
         return self.eval_loss_sum(u, i, j, used) / n
 
+    def set_concurrency(self, max_pairs_in_flight):
+        check(lib.qmfb_bpr_set_concurrency(self._h, int(max_pairs_in_flight)))
+
     def last_epoch_ms(self):
         ms = C.c_float()
         check(lib.qmfb_bpr_last_epoch_ms(self._h, C.byref(ms)))

@@ -69,6 +69,7 @@ _SIG = {
                                  C.POINTER(c_i64)]),
     "qmfb_bpr_update_triplets": (C.c_int, [vp, p_i32, p_i32, p_i32, c_i64, c_f64, c_f64, c_f64, c_f64]),
     "qmfb_bpr_eval_loss": (C.c_int, [vp, p_i32, p_i32, p_i32, c_i64, C.POINTER(c_f64)]),
+    "qmfb_bpr_set_concurrency": (C.c_int, [vp, c_i64]),
     "qmfb_bpr_last_epoch_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "qmfb_bpr_factors_device": (vp, [vp, C.c_int]),
     "qmfb_bpr_biases_device": (vp, [vp]),

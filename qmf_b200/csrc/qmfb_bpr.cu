@@ -53,7 +53,22 @@ struct qmfb_bpr {
   float epoch_ms = 0.f;
   int64_t launches = 0;
   int sms = 148;
+  int64_t max_warps = 0;  // 0 = automatic (see bpr_concurrency)
 };
+
+// Number of pairs processed concurrently (one warp each).  Every in-flight triplet computes its
+// step from values that do not yet contain the other in-flight steps, so the steps landing on
+// one row behave like ONE step with the learning rate multiplied by their count: with the
+// whole GPU in flight on a small catalogue (e.g. 17 000 warps on 300 items) SGD diverges.
+// Keeping at most ~min(nusers, nitems) / 2 pairs in flight bounds the expected number of
+// concurrent steps per row by ~1 for the uniformly sampled negative (2 item rows per triplet);
+// large catalogues use the whole machine.
+static int64_t bpr_concurrency(const qmfb_bpr* h) {
+  const int64_t hw = int64_t(h->sms) * 64;  // 64 resident warps per SM
+  if (h->max_warps > 0) return std::min<int64_t>(h->max_warps, hw);
+  const int64_t rows = std::min(h->n[0], h->n[1]);
+  return std::max<int64_t>(32, std::min<int64_t>(hw, rows / 2));
+}
 
 static constexpr int kLossBlocks = 1184;  // 8 CTAs per SM on 148 SMs
 
@@ -238,8 +253,8 @@ int qmfb_bpr_epoch(qmfb_bpr_t* h, double lr, double user_lambda, double item_lam
   }
   if (uint64_t(h->npairs) >= (1ull << 32)) return set_error(QMFB_ERR_UNSUPPORTED, "more than 2^32 training pairs");
   QMFB_CUDA(cudaMemsetAsync(h->error, 0, sizeof(int32_t), h->stream));
-  const int64_t warps_needed = h->npairs;
-  const int blocks = int(std::min<int64_t>((warps_needed + 7) / 8, int64_t(h->sms) * 8));
+  const int64_t warps = std::min<int64_t>(h->npairs, bpr_concurrency(h));
+  const int blocks = int((warps + 7) / 8);
   QMFB_CUDA(cudaEventRecord(h->ev[0], h->stream));
   switch ((h->k + 31) / 32) {
     case 1: bpr_epoch_kernel<1><<<blocks, 256, 0, h->stream>>>(p); break;
@@ -317,6 +332,12 @@ int qmfb_bpr_eval_loss(qmfb_bpr_t* h, const int32_t* u, const int32_t* i, const 
   h->launches += 2;
   QMFB_CUDA(cudaMemcpyAsync(sum_out, h->sum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   QMFB_CUDA(cudaStreamSynchronize(h->stream));
+  return QMFB_OK;
+}
+
+int qmfb_bpr_set_concurrency(qmfb_bpr_t* h, int64_t max_pairs_in_flight) {
+  if (!h || max_pairs_in_flight < 0) return set_error(QMFB_ERR_INVALID, "qmfb_bpr_set_concurrency: bad argument");
+  h->max_warps = max_pairs_in_flight;
   return QMFB_OK;
 }
 
