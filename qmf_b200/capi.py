@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqmf_b200.so")
+LIB_PATH = os.environ.get("QMFB_LIB", os.path.join(_HERE, "libqmf_b200.so"))  # QMFB_LIB: debug builds only
 
 SIDE_USER = 0
 SIDE_ITEM = 1

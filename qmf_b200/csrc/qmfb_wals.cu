@@ -60,6 +60,23 @@ using namespace qmfb;
 
 extern "C" {
 
+#ifdef QMFB_PROFILE_PHASES
+// debug build only (not part of include/qmf_b200.h): read and reset the phase cycle counters
+int qmfb_debug_phase_cycles(unsigned long long* out16) {
+  QMFB_CUDA(cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(unsigned long long) * 16));
+  unsigned long long zero[16] = {0};
+  QMFB_CUDA(cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)));
+  return QMFB_OK;
+}
+#endif
+
+#ifdef QMFB_PROFILE_PHASES
+int qmfb_debug_set_flags(int flags) {
+  QMFB_CUDA(cudaMemcpyToSymbol(g_debug_flags, &flags, sizeof(int)));
+  return QMFB_OK;
+}
+#endif
+
 int qmfb_padded_k(int k) {
   if (k < 1 || k > 128) return set_error(QMFB_ERR_UNSUPPORTED, "nfactors must be in [1, 128] (got %d)", k);
   return ((k + 31) / 32) * 32;

@@ -298,6 +298,19 @@ struct SolveParams {
   int* error;             // set to 1 if a pivot is not positive (reference: CHECK_EQ(result, 0), Matrix.cpp:94)
 };
 
+#ifdef QMFB_PROFILE_PHASES
+// debug build only: thread 0 of every CTA accumulates clock64() deltas per phase into
+// g_phase_cycles[phase] (build, tile store, factor (warp 0), panel, trailing/wait, back
+// substitution, tail) and g_phase_cycles[15] counts rows
+__device__ unsigned long long g_phase_cycles[16];
+__device__ int g_debug_flags;  // bit 0: skip the trailing updates of the non-diagonal warps (timing experiments only)
+#define QMFB_T(var) const long long var = clock64()
+#define QMFB_ACC(idx, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[idx], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define QMFB_T(var)
+#define QMFB_ACC(idx, a, b)
+#endif
+
 // One warp: factor the 8x8 diagonal tile A = U^T U and write W = inv(U) (row-major, upper) to
 // wtile.  C-fragment layout: lane holds row lane/4, columns 2*(lane%4)+{0,1}; an identity is
 // eliminated alongside.  The elimination is FRACTION-FREE so that the pivot-to-pivot dependency
@@ -314,7 +327,9 @@ __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile,
   double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
   double S = 1.0, prS = 1.0;
   bool ok = true;
-#pragma unroll
+  // deliberately NOT unrolled: the body is ~60 instructions; unrolled (x8, ~7 KB) it does not stay
+  // in the instruction cache between the once-per-panel calls and costs ~2x (measured)
+#pragma unroll 1
   for (int j = 0; j < 8; ++j) {
     const int src = 4 * j;
     const double p = __shfl_sync(0xffffffffu, (j & 1) ? a1 : a0, src + (j >> 1));
@@ -331,12 +346,14 @@ __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile,
     const double sc = __hiloint2double((2046 - ((hi >> 20) & 0x7ff)) << 20, 0);
     if (r == j) prS = p * S;
     S *= pn;
-    if (r > j) {
-      a0 = fma(a0, pn, -((ur * uc0) * sc));
-      a1 = fma(a1, pn, -((ur * uc1) * sc));
-      e0 = fma(e0, pn, -((ur * ec0) * sc));
-      e1 = fma(e1, pn, -((ur * ec1) * sc));
-    }
+    // predicated (no divergent branch): rows <= j keep their values
+    const bool upd = r > j;
+    const double n0 = fma(a0, pn, -((ur * uc0) * sc)), n1 = fma(a1, pn, -((ur * uc1) * sc));
+    const double m0 = fma(e0, pn, -((ur * ec0) * sc)), m1 = fma(e1, pn, -((ur * ec1) * sc));
+    a0 = upd ? n0 : a0;
+    a1 = upd ? n1 : a1;
+    e0 = upd ? m0 : e0;
+    e1 = upd ? m1 : e1;
   }
   const double g = rsqrt(prS);
   wtile[(2 * q) * 8 + r] = e0 * g;
@@ -507,8 +524,11 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       const int sn = slot_of(it + 1);
       if (sn < prm.nrows) nrow = __ldg(prm.order + sn);
     }
+    QMFB_T(tp0);
     const double csum = build_row<NT>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k,
                                       cs->p0, cs->p1, cs->base);
+    QMFB_T(tp1);
+    QMFB_ACC(0, tp0, tp1);
     int64_t np0 = 0, np1 = 0;
     if (tid == 0 && nrow >= 0) {
       np0 = __ldg(prm.row_ptr + nrow);
@@ -526,9 +546,16 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
     }
     // ---- blocked Cholesky, panel width 8; forward substitution rides along in column NT ------
     bool ok = true;
+    QMFB_T(tp2);
+    QMFB_ACC(1, tp1, tp2);
     if (warp == 0) ok = factor_diag_tile(tiles + size_t(SM::tidx(0, 0)) * 64, wt, lane);
+    QMFB_T(tp3);
+    QMFB_ACC(2, tp2, tp3);
     for (int I = 0; I < NT; ++I) {
+      QMFB_T(ts0);
       __syncthreads();  // W_I ready, row I of tiles final up to panel I-1
+      QMFB_T(ts1);
+      QMFB_ACC(4, ts0, ts1);
       // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+1 .. NT
       {
         const double w0 = wt[I * 64 + fo], w1 = wt[I * 64 + fo + 32];
@@ -541,8 +568,12 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
           *reinterpret_cast<double2*>(t + lane * 2) = make_double2(c[0], c[1]);
         }
       }
+      QMFB_T(ts2);
+      QMFB_ACC(3, ts1, ts2);
       if (I == NT - 1) break;
       __syncthreads();
+      QMFB_T(ts3);
+      QMFB_ACC(5, ts2, ts3);
       // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT.
       //     One warp updates the next diagonal tile first and factors it right away (look-ahead)
       //     while the other warps sweep the rest, four independent tiles at a time.
@@ -561,8 +592,15 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
         dmma(c, -u1, u1);
         *reinterpret_cast<double2*>(t + lane * 2) = make_double2(c[0], c[1]);
         __syncwarp();
+        QMFB_T(tf0);
         ok = factor_diag_tile(t, wt + (I + 1) * 64, lane) && ok;
+        QMFB_T(tf1);
+        QMFB_ACC(2, tf0, tf1);
+        QMFB_ACC(6, ts3, tf0);
       }
+#ifdef QMFB_PROFILE_PHASES
+      if ((g_debug_flags & 1) == 0)
+#endif
       if (SM::NWARPS == 1 || warp != dwarp) {
         // flat enumeration of the trailing tiles (contiguous in storage); (J1, J2) decoded incrementally
         int J1 = I + 1, off = 1 + wslot;  // position `off` inside row J1 (row J1 has NT - J1 + 1 tiles)
@@ -601,6 +639,8 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       }
     }
     if (!ok && lane == 0) *prm.error = 1;
+    QMFB_T(tp4);
+    QMFB_ACC(7, tp3, tp4);
 
     // ---- back substitution U x = z: thread t < KP keeps r_t in a register; per block step one
     //      8x8 mat-vec by inv(U_JJ) and one rank-8 update of the rows above -----------------------
@@ -640,6 +680,8 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       }
     }
     __syncthreads();
+    QMFB_T(tp5);
+    QMFB_ACC(8, tp4, tp5);
     // ---- loss term: c + x^T B x - 2 x^T b with x^T B x = z^T z - lambda x^T x (WALSEngine.cpp:295-304)
     if (warp == 0) {
       double part = 0.0;
@@ -666,6 +708,12 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
     }
     ++it;
     __syncthreads();  // tiles / xvec / bcopy free again, next row slot visible
+    QMFB_T(tp6);
+    QMFB_ACC(9, tp5, tp6);
+    QMFB_ACC(10, tp0, tp6);
+#ifdef QMFB_PROFILE_PHASES
+    if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[15], 1ull);
+#endif
   }
 }
 
