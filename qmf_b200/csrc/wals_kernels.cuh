@@ -298,18 +298,7 @@ struct SolveParams {
   int* error;             // set to 1 if a pivot is not positive (reference: CHECK_EQ(result, 0), Matrix.cpp:94)
 };
 
-#ifdef QMFB_PROFILE_PHASES
-// debug build only: thread 0 of every CTA accumulates clock64() deltas per phase into
-// g_phase_cycles[phase] (build, tile store, factor (warp 0), panel, trailing/wait, back
-// substitution, tail) and g_phase_cycles[15] counts rows
-__device__ unsigned long long g_phase_cycles[16];
-__device__ int g_debug_flags;  // bit 0: skip the trailing updates of the non-diagonal warps (timing experiments only)
-#define QMFB_T(var) const long long var = clock64()
-#define QMFB_ACC(idx, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[idx], (unsigned long long)((b) - (a))); } while (0)
-#else
-#define QMFB_T(var)
-#define QMFB_ACC(idx, a, b)
-#endif
+
 
 // One warp: factor the 8x8 diagonal tile A = U^T U and write W = inv(U) (row-major, upper) to
 // wtile.  C-fragment layout: lane holds row lane/4, columns 2*(lane%4)+{0,1}; an identity is
@@ -360,6 +349,19 @@ __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile,
   wtile[(2 * q + 1) * 8 + r] = e1 * g;
   return ok;
 }
+
+#ifdef QMFB_PROFILE_PHASES
+// debug build only: thread 0 of every CTA accumulates clock64() deltas per phase into
+// g_phase_cycles[phase] (build, tile store, factor (warp 0), panel, trailing/wait, back
+// substitution, tail) and g_phase_cycles[15] counts rows
+__device__ unsigned long long g_phase_cycles[16];
+__device__ int g_debug_flags;  // bit 0: skip the trailing updates of the non-diagonal warps (timing experiments only)
+#define QMFB_T(var) const long long var = clock64()
+#define QMFB_ACC(idx, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[idx], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define QMFB_T(var)
+#define QMFB_ACC(idx, a, b)
+#endif
 
 // Build phase of one row.  The kernel keeps its per-row schedule state in shared memory, so only
 // the accumulators and the loader state are live here; that leaves the register allocator room
@@ -434,12 +436,22 @@ __device__ __forceinline__ double build_row(unsigned char* smem, const double* _
   const uint32_t lim = base + uint32_t(nch);  // the ring is reused as tile storage: no cross-row prefetch
   for (int c = 0; c < nch; ++c) {
     const uint32_t gc = base + c;
-    while (issued < lim && issued < gc + kStages) issue_one();
+    // refill the stage that was consumed TWO iterations ago (prefetch distance kStages - 2): its
+    // empty barrier completed long ago, so no warp ever waits for the slowest warp of the
+    // previous chunk (with distance kStages - 1 every chunk starts with a CTA-wide soft barrier)
+    QMFB_T(tb0);
+    while (issued < lim && issued + 1 < gc + kStages) issue_one();
     const uint32_t st = gc % kStages;
+    QMFB_T(tb1);
     mbar_wait(&full[st], (gc / kStages) & 1u);
+    QMFB_T(tb2);
     const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
     const double* w8 = wts + st * 2 * kChunk;
     chunk_mma_dispatch<NT, 0>(warp, acc, sb, w8, lane);
+    QMFB_T(tb3);
+    QMFB_ACC(11, tb0, tb1);
+    QMFB_ACC(12, tb1, tb2);
+    QMFB_ACC(13, tb2, tb3);
 #pragma unroll
     for (int s = 0; s < kChunk / 2; s += 2) {  // two independent chains
       bacc += w8[kChunk + 2 * s + bh] * sb[(2 * s + bh) * SM::LD + bi];
@@ -447,6 +459,8 @@ __device__ __forceinline__ double build_row(unsigned char* smem, const double* _
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
+    QMFB_T(tb4);
+    QMFB_ACC(14, tb3, tb4);
   }
   __syncthreads();  // every warp is done reading the ring before the tiles overwrite it
   // tiles to shared memory: A(i,i) += lambda (WALSEngine.cpp:290-292), unit pivot on padding

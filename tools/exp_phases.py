@@ -10,7 +10,8 @@ K = CudaKernels()
 k = 128
 kp = K.padded_k(k)
 names = ["build", "tile store+b", "factor diag (warp0)", "panel (b)", "wait top-of-step", "wait after panel", "diag tile update",
-         "cholesky total", "back substitution", "loss/store/next", "row total"]
+         "cholesky total", "back substitution", "loss/store/next", "row total", "  build: issue_one", "  build: wait full",
+         "  build: chunk_mma", "  build: b-acc + arrive"]
 K.lib.qmfb_debug_set_flags(int(os.environ.get("EXP_FLAGS", "0")))
 for spec in sys.argv[1:]:
     nrows, nnz_row, ncols = (int(x) for x in spec.split(","))
