@@ -127,8 +127,8 @@ struct WalsSmem {
   static constexpr size_t kOffB = kOffW + size_t(NT) * 64 * 8;               // b copy (KP)
   static constexpr size_t kOffX = kOffB + size_t(KP) * 8;                    // x (KP)
   static constexpr size_t kOffR = kOffX + size_t(KP) * 8;                    // back-substitution rhs (8)
-  static constexpr size_t kOffBh = kOffR + 64;                               // b half sums (2*KP)
-  static constexpr size_t kOffBar = kOffBh + size_t(KP) * 16;                // full[kStages], empty[kStages]
+  static constexpr size_t kOffBh = kOffR + 64;                               // per-warp partial b (NWARPS*KP) + csum (NWARPS)
+  static constexpr size_t kOffBar = kOffBh + size_t(NWARPS) * (KP + 1) * 8;  // full[kStages], empty[kStages]
   static constexpr size_t kOffRow = kOffBar + size_t(kStages) * 16;          // 2 row slots x 32 bytes
   static constexpr size_t kBytes = kOffRow + 64;
 
@@ -364,63 +364,74 @@ __device__ int g_debug_flags;  // bit 0: skip the trailing updates of the non-di
 #endif
 
 // Build phase of one row.  The kernel keeps its per-row schedule state in shared memory, so only
-// the accumulators and the loader state are live here; that leaves the register allocator room
-// to keep several DMMA fragments in flight under the 128-register cap of a 2-CTA/SM launch
-// (with ~25 more live registers ptxas serialises LDS -> DMMA -> LDS through one register).
+// the accumulators and a little loader state are live here.
 // Gathers rows col[p0..p1) of Y through the cp.async ring, accumulates
 //   A = G + sum_s (alpha r_s) y_s y_s^T   (upper tiles)      b = sum_s (1 + alpha r_s) y_s
-// (WALSEngine.cpp:277-287), adds lambda to the diagonal (:290-292) and leaves the tiles and the
-// two half sums of b in shared memory.  Returns this thread's share of sum_s (1 + alpha r_s).
+// (WALSEngine.cpp:277-287), adds lambda to the diagonal (:290-292) and leaves the tiles, the
+// per-warp partial sums of b and of sum_s (1 + alpha r_s) in shared memory.
+//
+// All non-DMMA work of a chunk is done by ONE warp, in rotation: warp (n mod NWARPS) gathers
+// chunk n (32 x 16-byte cp.async per lane, weights, index prefetch) and accumulates b for it,
+// the other warps do nothing but wait -> 4 k4-steps of DMMA -> release.  With every warp doing
+// 1/NWARPS of the bookkeeping of every chunk (the first version) all warps left the DMMA pipe at
+// the same time each chunk: measured 885 + 782 cycles of bookkeeping per chunk and warp around
+// 1 088 cycles' worth of DMMA issue, tensor pipe 69 % busy (tools/exp_phases.py).
 template <int NT>
-__device__ __forceinline__ double build_row(unsigned char* smem, const double* __restrict__ Y, int64_t ldy,
-                                         const int32_t* __restrict__ col, const double* __restrict__ val,
-                                         const double* __restrict__ gram, double alpha, double lambda, int k,
-                                         int64_t p0, int64_t p1, uint32_t base) {
+__device__ __forceinline__ void build_row(unsigned char* smem, const double* __restrict__ Y, int64_t ldy,
+                                          const int32_t* __restrict__ col, const double* __restrict__ val,
+                                          const double* __restrict__ gram, double alpha, double lambda, int k,
+                                          int64_t p0, int64_t p1, uint32_t base) {
   using SM = WalsSmem<NT>;
   double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
   double* tiles = reinterpret_cast<double*>(smem + SM::kOffTiles);
   double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
-  double* bhalf = reinterpret_cast<double*>(smem + SM::kOffBh);
+  double* bpart = reinterpret_cast<double*>(smem + SM::kOffBh);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* empty = full + kStages;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  constexpr int TPR = SM::KP / 2;  // threads per gathered row (16 bytes each); 4 rows per pass
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int PPR = SM::KP / 2;             // 16-byte pieces per gathered row
+  constexpr int NCOPY = kChunk * PPR / 32;    // cp.async per lane per chunk
+  constexpr int NBC = SM::KP / 32;            // b columns per lane
+  constexpr int kAhead = kStages - 2;         // chunks in flight beyond the one being consumed
   const int nch = int((p1 - p0 + kChunk - 1) / kChunk);
+  const uint32_t lim = base + uint32_t(nch);  // the ring is reused as tile storage: no cross-row prefetch
 
-  uint32_t issued = base;  // absolute index of the next chunk to issue (stage = index % kStages)
-  int32_t pcol = 0;        // lanes < kChunk: column of row `lane` of chunk `issued`
-  double pval = 0.0;       // warp 0, lanes < kChunk: its rating
+  // loader state of THIS warp: the next chunk (absolute index, == warp mod NWARPS) it gathers
+  uint32_t mine = base + (uint32_t(warp) + SM::NWARPS - base % SM::NWARPS) % SM::NWARPS;
+  int32_t pcol = 0;   // lanes < kChunk: column of row `lane` of chunk `mine`
+  double pval = 0.0;
   bool pvalid = false;
-  double csum = 0.0;       // warp 0, lanes < kChunk: sum of (1 + alpha r), WALSEngine.cpp:286
+  double csum = 0.0, bcol[NBC];
+#pragma unroll
+  for (int j = 0; j < NBC; ++j) bcol[j] = 0.0;
   auto prefetch_idx = [&]() {
-    const int64_t p = p0 + int64_t(issued - base) * kChunk + lane;
-    pvalid = lane < kChunk && p < p1;
+    const int64_t p = p0 + int64_t(mine - base) * kChunk + lane;
+    pvalid = lane < kChunk && mine < lim && p < p1;
     pcol = pvalid ? __ldg(col + p) : 0;
-    pval = (pvalid && tid < kChunk) ? __ldg(val + p) : 0.0;
+    pval = pvalid ? __ldg(val + p) : 0.0;
   };
-  auto issue_one = [&]() {
-    const uint32_t st = issued % kStages;
-    if (issued >= kStages) mbar_wait(&empty[st], ((issued / kStages) & 1u) ^ 1u);
-    if (tid < kChunk) {
-      const double wa = pvalid ? alpha * pval : 0.0;        // WALSEngine.cpp:282  alpha * r
+  auto issue_mine = [&]() {
+    const uint32_t st = mine % kStages;
+    if (mine >= kStages) mbar_wait(&empty[st], ((mine / kStages) & 1u) ^ 1u);
+    if (lane < kChunk) {
       const double wb = pvalid ? 1.0 + alpha * pval : 0.0;  // WALSEngine.cpp:280  1 + alpha * r
-      wts[st * 2 * kChunk + lane] = wa;
+      wts[st * 2 * kChunk + lane] = pvalid ? alpha * pval : 0.0;  // WALSEngine.cpp:282  alpha * r
       wts[st * 2 * kChunk + kChunk + lane] = wb;
       csum += wb;
       mbar_arrive(&full[st]);
     }
-    const int rsub = tid / TPR, piece = tid % TPR;
-#pragma unroll
-    for (int m = 0; m < kChunk / 4; ++m) {
-      const int row = 4 * m + rsub;
+#pragma unroll 8
+    for (int m = 0; m < NCOPY; ++m) {
+      const int q = lane + 32 * m, row = q / PPR, piece = q % PPR;
       const int32_t c = __shfl_sync(0xffffffffu, pcol, row);
       cp_async16(stagebuf + (size_t(st) * kChunk + row) * SM::LD + piece * 2, Y + int64_t(c) * ldy + piece * 2);
     }
     cp_async_arrive(&full[st]);
-    ++issued;
+    mine += SM::NWARPS;
     prefetch_idx();
   };
   prefetch_idx();
+  if (mine < lim && mine < base + kAhead) issue_mine();  // prologue: the first kAhead chunks of the row
 
   double acc[NT + 1][2];
 #pragma unroll
@@ -431,17 +442,10 @@ __device__ __forceinline__ double build_row(unsigned char* smem, const double* _
     acc[t][0] = g.x;
     acc[t][1] = g.y;
   }
-  double bacc = 0.0, bacc2 = 0.0;
-  const int bi = tid % SM::KP, bh = tid / SM::KP;
-  const uint32_t lim = base + uint32_t(nch);  // the ring is reused as tile storage: no cross-row prefetch
   for (int c = 0; c < nch; ++c) {
-    const uint32_t gc = base + c;
-    // refill the stage that was consumed TWO iterations ago (prefetch distance kStages - 2): its
-    // empty barrier completed long ago, so no warp ever waits for the slowest warp of the
-    // previous chunk (with distance kStages - 1 every chunk starts with a CTA-wide soft barrier)
-    QMFB_T(tb0);
-    while (issued < lim && issued + 1 < gc + kStages) issue_one();
-    const uint32_t st = gc % kStages;
+    const uint32_t gc = base + c, st = gc % kStages;
+    // the stage refilled here was consumed TWO chunks ago: its empty barrier completed long ago
+    if (mine == gc + kAhead && mine < lim) issue_mine();
     QMFB_T(tb1);
     mbar_wait(&full[st], (gc / kStages) & 1u);
     QMFB_T(tb2);
@@ -449,19 +453,26 @@ __device__ __forceinline__ double build_row(unsigned char* smem, const double* _
     const double* w8 = wts + st * 2 * kChunk;
     chunk_mma_dispatch<NT, 0>(warp, acc, sb, w8, lane);
     QMFB_T(tb3);
-    QMFB_ACC(11, tb0, tb1);
-    QMFB_ACC(12, tb1, tb2);
-    QMFB_ACC(13, tb2, tb3);
+    if (int(gc % SM::NWARPS) == warp) {  // this chunk's b accumulation is ours
+#pragma unroll 4
+      for (int s = 0; s < kChunk; ++s) {
+        const double w = w8[kChunk + s];
 #pragma unroll
-    for (int s = 0; s < kChunk / 2; s += 2) {  // two independent chains
-      bacc += w8[kChunk + 2 * s + bh] * sb[(2 * s + bh) * SM::LD + bi];
-      bacc2 += w8[kChunk + 2 * s + 2 + bh] * sb[(2 * s + 2 + bh) * SM::LD + bi];
+        for (int j = 0; j < NBC; ++j) bcol[j] += w * sb[s * SM::LD + lane + 32 * j];
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
     QMFB_T(tb4);
+    QMFB_ACC(12, tb1, tb2);
+    QMFB_ACC(13, tb2, tb3);
     QMFB_ACC(14, tb3, tb4);
   }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+#pragma unroll
+  for (int j = 0; j < NBC; ++j) bpart[warp * SM::KP + lane + 32 * j] = bcol[j];
+  if (lane == 0) bpart[SM::NWARPS * SM::KP + warp] = csum;
   __syncthreads();  // every warp is done reading the ring before the tiles overwrite it
   // tiles to shared memory: A(i,i) += lambda (WALSEngine.cpp:290-292), unit pivot on padding
   const int r = lane >> 2, c0 = 2 * (lane & 3);
@@ -477,8 +488,6 @@ __device__ __forceinline__ double build_row(unsigned char* smem, const double* _
     }
     *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(I, J)) * 64 + lane * 2) = make_double2(v0, v1);
   }
-  bhalf[tid] = bacc + bacc2;
-  return csum;
 }
 
 template <int NT>
@@ -500,7 +509,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], SM::NTHREADS + kChunk);  // one deferred cp.async arrival per thread + weight writers
+      mbar_init(&full[s], 32 + kChunk);  // gathering warp: one deferred cp.async arrival per lane + weight writers
       mbar_init(&empty[s], SM::NWARPS);
     }
     mbar_fence_init();
@@ -539,8 +548,8 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       if (sn < prm.nrows) nrow = __ldg(prm.order + sn);
     }
     QMFB_T(tp0);
-    const double csum = build_row<NT>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k,
-                                      cs->p0, cs->p1, cs->base);
+    build_row<NT>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k, cs->p0, cs->p1,
+                  cs->base);
     QMFB_T(tp1);
     QMFB_ACC(0, tp0, tp1);
     int64_t np0 = 0, np1 = 0;
@@ -549,9 +558,11 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       np1 = __ldg(prm.row_ptr + nrow + 1);
     }
     __syncthreads();
-    // b = sum of the two half sums; b column tiles (column 0 = b, other columns 0); keep a copy
+    // b = sum of the per-warp partial sums; b column tiles (column 0 = b, other columns 0); keep a copy
     if (tid < SM::KP) {
-      const double b = bhalf[tid] + bhalf[tid + SM::KP];
+      double b = 0.0;
+#pragma unroll
+      for (int w = 0; w < SM::NWARPS; ++w) b += bhalf[w * SM::KP + tid];
       bcopy[tid] = b;
       double* bt = tiles + size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8;
       bt[0] = b;
@@ -704,7 +715,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
         const double x = xvec[i];
         part += z * z - prm.lambda * x * x - 2.0 * x * bcopy[i];
       }
-      part += csum;
+      if (lane < SM::NWARPS) part += bhalf[SM::NWARPS * SM::KP + lane];  // sum_s (1 + alpha r_s), WALSEngine.cpp:286
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
       if (lane == 0) prm.row_loss[cs->row] = part;
