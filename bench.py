@@ -264,6 +264,41 @@ def run_bpr_reference(threads):
             "sample": "2 epochs of BPREngine::optimize on the C2 shape, num_hogwild_threads = nthreads = %d" % threads}
 
 
+def run_eval_ours(device=0):
+    """north_star part 3: all-item scoring + rank statistics (eval_rank_kernel) on the C2 shape, all users"""
+    import torch
+    from qmf_b200 import capi
+    nu, ni, k, npos = 10_000, 5_000, 30, 5
+    dev = torch.device("cuda", device)
+    g = torch.Generator(device=dev).manual_seed(3)
+    U = torch.rand(nu, k, generator=g, device=dev, dtype=torch.float64) - 0.5
+    V = torch.rand(ni, k, generator=g, device=dev, dtype=torch.float64) - 0.5
+    bias = torch.rand(ni, generator=g, device=dev, dtype=torch.float64) - 0.5
+    tu = torch.arange(nu, device=dev, dtype=torch.int32)
+    lp = torch.arange(nu + 1, device=dev, dtype=torch.int64) * npos
+    li = (torch.sort(torch.rand(nu, ni, generator=g, device=dev).topk(npos, dim=1).indices, dim=1).values).to(torch.int32).reshape(-1).contiguous()
+    cnt = torch.zeros(nu * npos + nu, device=dev, dtype=torch.int32)
+    sc = torch.zeros(nu * npos, device=dev, dtype=torch.float64)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ms = []
+    for _ in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        capi.check(capi.lib.qmfb_eval_rank_dev(st, U.data_ptr(), k, V.data_ptr(), k, ni, k, bias.data_ptr(), tu.data_ptr(), nu,
+                                               lp.data_ptr(), li.data_ptr(), nu * npos, cnt.data_ptr(), sc.data_ptr(),
+                                               err.data_ptr()))
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    t = min(ms[1:]) * 1e-3
+    assert int(cnt.sum()) == nu * (ni - npos)
+    return {"shape": {"test_users": nu, "nitems": ni, "nfactors": k, "positives_per_user": npos}, "ms": t * 1e3,
+            "user_item_scores_per_s": nu * ni / t, "gflops": 2.0 * nu * ni * k / t * 1e-9,
+            "note": "exact-order FP64 mul+add (no FMA) so that scores are bit-identical to the reference; 3 launches "
+                    "(2 memsets + eval_rank_kernel)"}
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -345,7 +380,11 @@ def run_ours(args, cfg, workload):
     roofline = {
         "kernel": "wals_solve_kernel<16> (2 launches/epoch: user rows, item rows)",
         "bound": "tensor", "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-        "frac": achieved_tf / FP64_PEAK_TFLOPS, "traffic": None,
+        "frac": achieved_tf / FP64_PEAK_TFLOPS,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the user-rows launch (profiles/r01_solve_final_ncu.csv:
+        # 1.40 GB + 0.50 GB vs 1.71 GB algorithmic: the gathered item factors stay in L2); ncu reports no DRAM
+        # counters for the item-rows launch of the same capture
+        "traffic": 1.90e9 if (workload.startswith("C4") and world == 1) else None,
         "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json "
                        "has no FP64 entry (its bf16 figure does not apply to an FP64 kernel)",
         "algorithmic_flops_per_epoch": fl, "solve_ms_user_item": [float(np.mean([x[0] for x in solve_ms])),
@@ -430,6 +469,7 @@ def run_ours(args, cfg, workload):
             bpr[shape] = r
         if not args.no_cpu_baseline:
             bpr["cpu_baseline_c2"] = run_bpr_reference(os.cpu_count() or 1)
+    evalr = run_eval_ours(local_rank) if (rank == 0 and world == 1 and not args.no_bpr) else None
 
     if rank == 0:
         line = {
@@ -440,7 +480,7 @@ def run_ours(args, cfg, workload):
                        "lambda": LAMBDA, "parallelism": "rows x%d" % world,
                        "l2": "inputs (2.9 GB) larger than the 126 MB L2; no flush"},
             "loss": loss_value, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
-            "cpu_baseline": cpu_baseline, "bpr": bpr, "lib": os.path.relpath(capi.LIB_PATH, ROOT),
+            "cpu_baseline": cpu_baseline, "bpr": bpr, "eval": evalr, "lib": os.path.relpath(capi.LIB_PATH, ROOT),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
