@@ -337,8 +337,11 @@ __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile,
     S *= pn;
     // predicated (no divergent branch): rows <= j keep their values
     const bool upd = r > j;
-    const double n0 = fma(a0, pn, -((ur * uc0) * sc)), n1 = fma(a1, pn, -((ur * uc1) * sc));
-    const double m0 = fma(e0, pn, -((ur * ec0) * sc)), m1 = fma(e1, pn, -((ur * ec1) * sc));
+    // 9 FP64 instructions per step: under a co-resident CTA's DMMA stream every FP64 instruction
+    // of this warp waits for a pipe slot, so their COUNT (not only the dependency chain) is the cost
+    const double us = -(ur * sc);
+    const double n0 = fma(a0, pn, us * uc0), n1 = fma(a1, pn, us * uc1);
+    const double m0 = fma(e0, pn, us * ec0), m1 = fma(e1, pn, us * ec1);
     a0 = upd ? n0 : a0;
     a1 = upd ? n1 : a1;
     e0 = upd ? m0 : e0;
