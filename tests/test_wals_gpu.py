@@ -137,3 +137,67 @@ def test_epoch_host_roundtrip(oracle_lib):
     lo = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, 30, icsr[0], icsr[1], icsr[2], 40.0, 0.05, NU, NI, 16)
     assert rel_err(Xo, X) < FACTOR_TOL and rel_err(Yo, Y) < FACTOR_TOL
     assert abs(loss - lo) <= LOSS_TOL * abs(lo)
+
+
+def test_sharded_driver_single_rank_matches_oracle(oracle_lib):
+    """the kernel-level ABI (device pointers, caller-owned torch tensors) used by the multi-GPU driver"""
+    import torch
+    from qmf_b200 import csr_from_coo
+    from qmf_b200.wals_dist import ShardedWals
+    u, i, v = uniform_dataset(220, 140, 4000, 31, id_scale=(5, 2), dup=12)
+    uids, urp, uci, uv = csr_from_coo(u, i, v)
+    iids, irp, ici, iv = csr_from_coo(i, u, v)
+    NU, NI, k = len(uids), len(iids), 64
+    dev = torch.device("cuda", 0)
+    t = lambda a: tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in a)
+    sw = ShardedWals(NU, NI, k, t((urp, uci, uv)), t((irp, ici, iv)), dev)
+    Y0 = init_factors(NI, k, seed=8)
+    sw.set_factors(1, Y0)
+    X, Y = np.zeros((NU, k)), Y0.copy()
+    for _ in range(2):
+        loss = float(sw.epoch(40.0, 0.05))
+        sw.check_error()
+        oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, urp, uci, uv, 40.0, 0.05, NU, NI, 16)
+        lo = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, irp, ici, iv, 40.0, 0.05, NU, NI, 16)
+        assert rel_err(sw.get_factors(0).cpu().numpy(), X) < FACTOR_TOL
+        assert rel_err(sw.get_factors(1).cpu().numpy(), Y) < FACTOR_TOL
+        assert abs(loss - lo) <= LOSS_TOL * abs(lo)
+
+
+def test_full_size_properties_c3():
+    """BASELINE config C3 (138k x 27k, 20M nnz, k=64) at full size: properties that do not need the
+    oracle - (1) every sampled row satisfies its normal equations (G + sum alpha r y y^T + lambda I) x = b
+    to 1e-10, (2) the kernel is deterministic (a repeated half-step is bit-identical), (3) the loss
+    equals sum_rows [c + x^T(A - lambda I)x - 2 x^T b] evaluated on the host for the sampled rows."""
+    import torch
+    from qmf_b200.datagen import CONFIGS, init_item_factors, uniform_csr_torch
+    from qmf_b200.wals_dist import ShardedWals
+    nu, ni, nnz, k = CONFIGS["c3"]
+    dev = torch.device("cuda", 0)
+    csr_user, csr_item = uniform_csr_torch(nu, ni, nnz, seed=99, device=dev)
+    sw = ShardedWals(nu, ni, k, csr_user, csr_item, dev)
+    sw.set_factors(1, init_item_factors(ni, k, seed=1))
+    alpha, lam = 40.0, 0.05
+    sw.epoch(alpha, lam)
+    sw.check_error()
+    Y = sw.get_factors(1).clone()            # fixed side of the next user half-step
+    sw.half_step(0, alpha, lam)
+    row_loss = sw.row_loss[:nu].clone()
+    X1 = sw.get_factors(0).clone()
+    sw.half_step(0, alpha, lam)              # same inputs (Y unchanged) -> identical bits
+    assert torch.equal(X1, sw.get_factors(0)) and torch.equal(row_loss, sw.row_loss[:nu])
+    Yh = Y.cpu().numpy()
+    G = Yh.T @ Yh
+    rp, col, val = (t.cpu().numpy() for t in csr_user)
+    rng = np.random.default_rng(0)
+    rows = np.concatenate([rng.integers(0, nu, 40), [int(np.argmax(np.diff(rp))), int(np.argmin(np.diff(rp)))]])
+    Xh, rl = X1.cpu().numpy(), row_loss.cpu().numpy()
+    for r in rows:
+        sl = slice(rp[r], rp[r + 1])
+        Ys, w = Yh[col[sl]], val[sl]
+        B = G + (Ys * (alpha * w)[:, None]).T @ Ys
+        b = ((1 + alpha * w)[:, None] * Ys).sum(0)
+        x = Xh[r]
+        assert np.abs((B + lam * np.eye(k)) @ x - b).max() <= 1e-10 * np.abs(b).max(), r
+        want = (1 + alpha * w).sum() + x @ B @ x - 2 * x @ b
+        assert abs(rl[r] - want) <= 1e-11 * abs(want), (r, rl[r], want)
