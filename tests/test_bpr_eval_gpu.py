@@ -160,3 +160,36 @@ def test_rank_statistics_bit_exact(oracle_lib, nu, ni, k, biases):
             kind, kk = oracle.metric_kind(name)
             want = oracle_lib.qmfo_metric_one(kind, kk, labels, scores[t], ni)
             assert got[name] == want, (t, name, got[name], want)
+
+
+def test_non_finite_gradient_is_reported():
+    """CHECK(std::isfinite(e)) in BPREngine::update (qmf/bpr/BPREngine.cpp:184-185) aborts the
+    reference; the C ABI returns QMFB_ERR_NOT_FINITE."""
+    from qmf_b200 import capi
+    from qmf_b200.bpr import BprEngineHandle
+    h = BprEngineHandle(4, 6, 8)
+    P = np.full((4, 8), 1e200)
+    Q = np.zeros((6, 8))
+    Q[1] = 1e200                    # p_u . (q_1 - q_j) overflows to +inf -> exp(inf) = inf -> e = 0 is finite;
+    Q[2] = np.nan                   # a NaN row makes e NaN
+    h.set_factors(0, P)
+    h.set_factors(1, Q)
+    with pytest.raises(capi.QmfbError) as e:
+        h.update_triplets([0], [2], [3], 0.05, 0.025, 0.0025, 1.0)
+    assert e.value.code == capi.ERR_NOT_FINITE
+
+
+def test_unsupported_shapes_fail_loudly():
+    from qmf_b200 import capi
+    from qmf_b200.bpr import BprEngineHandle
+    from qmf_b200.wals import WalsEngineHandle
+    with pytest.raises(capi.QmfbError) as e:
+        WalsEngineHandle(10, 10, 129)
+    assert e.value.code == -5 and "nfactors" in str(e.value)
+    with pytest.raises(capi.QmfbError):
+        BprEngineHandle(10, 10, 200)
+    h = BprEngineHandle(3, 3, 4)
+    with pytest.raises(capi.QmfbError):
+        h.get_biases()              # "can't access bias when withBiases = false" (qmf/FactorData.h:45-48)
+    with pytest.raises(capi.QmfbError):
+        h.set_data([0, 5], [1, 1])  # user idx out of range
