@@ -127,7 +127,8 @@ struct WalsSmem {
   static constexpr size_t kOffB = kOffW + size_t(NT) * 64 * 8;               // b copy (KP)
   static constexpr size_t kOffX = kOffB + size_t(KP) * 8;                    // x (KP)
   static constexpr size_t kOffR = kOffX + size_t(KP) * 8;                    // back-substitution rhs (8)
-  static constexpr size_t kOffBh = kOffR + 64;                               // per-warp partial b (NWARPS*KP) + csum (NWARPS)
+  static constexpr size_t kOffFs = kOffR + 64;                               // pivot-row broadcast scratch (16 doubles)
+  static constexpr size_t kOffBh = kOffFs + 128;                             // per-warp partial b (NWARPS*KP) + csum (NWARPS)
   static constexpr size_t kOffBar = kOffBh + size_t(NWARPS) * (KP + 1) * 8;  // full[kStages], empty[kStages]
   static constexpr size_t kOffRow = kOffBar + size_t(kStages) * 16;          // 2 row slots x 32 bytes
   static constexpr size_t kBytes = kOffRow + 64;
@@ -309,39 +310,38 @@ struct SolveParams {
 // exact).  Row r of the true factor is recovered at the end with a single
 // g_r = rsqrt(p_r * S_r):  U[r][c] = a_rc * g_r,  inv(U)[c][r] = e_rc * g_r.
 // Returns false on a non-positive pivot (reference: dsysv info != 0, qmf/Matrix.cpp:94).
-__device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile, int lane) {
+__device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile, double* scratch, int lane) {
   const int r = lane >> 2, q = lane & 3;
   const double2 a = *reinterpret_cast<const double2*>(tile + lane * 2);
   double a0 = a.x, a1 = a.y;
   double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
   double S = 1.0, prS = 1.0;
   bool ok = true;
-  // deliberately NOT unrolled: the body is ~60 instructions; unrolled (x8, ~7 KB) it does not stay
-  // in the instruction cache between the once-per-panel calls and costs ~2x (measured)
+  // deliberately NOT unrolled (instruction-cache footprint).  The pivot row is broadcast through 16
+  // doubles of shared memory: 2 stores + 4 loads per step instead of 14 shuffles - the warp shares
+  // the SM's memory-instruction queue with the trailing updates of the other warps
 #pragma unroll 1
   for (int j = 0; j < 8; ++j) {
-    const int src = 4 * j;
-    const double p = __shfl_sync(0xffffffffu, (j & 1) ? a1 : a0, src + (j >> 1));
-    const double uc0 = __shfl_sync(0xffffffffu, a0, src + q);
-    const double uc1 = __shfl_sync(0xffffffffu, a1, src + q);
-    const double ec0 = __shfl_sync(0xffffffffu, e0, src + q);
-    const double ec1 = __shfl_sync(0xffffffffu, e1, src + q);
-    const double t0 = __shfl_sync(0xffffffffu, a0, src + (r >> 1));
-    const double t1 = __shfl_sync(0xffffffffu, a1, src + (r >> 1));
-    const double ur = (r & 1) ? t1 : t0;
+    if (r == j) {
+      *reinterpret_cast<double2*>(scratch + 2 * q) = make_double2(a0, a1);
+      *reinterpret_cast<double2*>(scratch + 8 + 2 * q) = make_double2(e0, e1);
+    }
+    __syncwarp();
+    const double p = scratch[j];
+    const double2 uc = *reinterpret_cast<const double2*>(scratch + 2 * q);
+    const double2 ec = *reinterpret_cast<const double2*>(scratch + 8 + 2 * q);
+    const double ur = scratch[r];
+    __syncwarp();
     ok = ok && (p > 0.0);
     const int hi = __double2hiint(p), lo = __double2loint(p);
     const double pn = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, lo);
     const double sc = __hiloint2double((2046 - ((hi >> 20) & 0x7ff)) << 20, 0);
     if (r == j) prS = p * S;
     S *= pn;
-    // predicated (no divergent branch): rows <= j keep their values
     const bool upd = r > j;
-    // 9 FP64 instructions per step: under a co-resident CTA's DMMA stream every FP64 instruction
-    // of this warp waits for a pipe slot, so their COUNT (not only the dependency chain) is the cost
     const double us = -(ur * sc);
-    const double n0 = fma(a0, pn, us * uc0), n1 = fma(a1, pn, us * uc1);
-    const double m0 = fma(e0, pn, us * ec0), m1 = fma(e1, pn, us * ec1);
+    const double n0 = fma(a0, pn, us * uc.x), n1 = fma(a1, pn, us * uc.y);
+    const double m0 = fma(e0, pn, us * ec.x), m1 = fma(e1, pn, us * ec.y);
     a0 = upd ? n0 : a0;
     a1 = upd ? n1 : a1;
     e0 = upd ? m0 : e0;
@@ -504,6 +504,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
   double* bcopy = reinterpret_cast<double*>(smem + SM::kOffB);
   double* xvec = reinterpret_cast<double*>(smem + SM::kOffX);
   double* rvec = reinterpret_cast<double*>(smem + SM::kOffR);
+  double* fscratch = reinterpret_cast<double*>(smem + SM::kOffFs);
   double* bhalf = reinterpret_cast<double*>(smem + SM::kOffBh);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* empty = full + kStages;
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
     bool ok = true;
     QMFB_T(tp2);
     QMFB_ACC(1, tp1, tp2);
-    if (warp == 0) ok = factor_diag_tile(tiles + size_t(SM::tidx(0, 0)) * 64, wt, lane);
+    if (warp == 0) ok = factor_diag_tile(tiles + size_t(SM::tidx(0, 0)) * 64, wt, fscratch, lane);
     QMFB_T(tp3);
     QMFB_ACC(2, tp2, tp3);
     for (int I = 0; I < NT; ++I) {
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
         *reinterpret_cast<double2*>(t + lane * 2) = make_double2(c[0], c[1]);
         __syncwarp();
         QMFB_T(tf0);
-        ok = factor_diag_tile(t, wt + (I + 1) * 64, lane) && ok;
+        ok = factor_diag_tile(t, wt + (I + 1) * 64, fscratch, lane) && ok;
         QMFB_T(tf1);
         QMFB_ACC(2, tf0, tf1);
         QMFB_ACC(6, ts3, tf0);

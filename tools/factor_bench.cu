@@ -82,7 +82,7 @@ __global__ void kern(double* out, long long* cyc, int iters) {
   bool ok = true;
   long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
-    if (V == 0) ok = factor_diag_tile(tile[warp], w[warp], lane) && ok;
+    if (V == 0) ok = factor_diag_tile(tile[warp], w[warp], scr[warp], lane) && ok;
     if (V == 1) ok = factor_noinv(tile[warp], w[warp], lane) && ok;
     if (V == 2) ok = factor_smem(tile[warp], w[warp], scr[warp], lane) && ok;
     __syncwarp();
