@@ -321,7 +321,7 @@ __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile,
   // doubles of shared memory: 2 stores + 4 loads per step instead of 14 shuffles - the warp shares
   // the SM's memory-instruction queue with the trailing updates of the other warps
 #pragma unroll 1
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 7; ++j) {
     if (r == j) {
       *reinterpret_cast<double2*>(scratch + 2 * q) = make_double2(a0, a1);
       *reinterpret_cast<double2*>(scratch + 8 + 2 * q) = make_double2(e0, e1);
@@ -346,6 +346,11 @@ __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile,
     a1 = upd ? n1 : a1;
     e0 = upd ? m0 : e0;
     e1 = upd ? m1 : e1;
+  }
+  {  // last pivot a_77 (lane 31, second slot): nothing left to eliminate, only row 7's scale needs it
+    const double p7 = __shfl_sync(0xffffffffu, a1, 31);
+    ok = ok && (p7 > 0.0);
+    if (r == 7) prS = p7 * S;
   }
   const double g = rsqrt(prS);
   wtile[(2 * q) * 8 + r] = e0 * g;
