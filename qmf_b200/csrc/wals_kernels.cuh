@@ -195,6 +195,17 @@ __device__ __forceinline__ void acc_tile(int warp, int t, int& I, int& J) {
   }
 }
 
+// 8x8 tiles in shared memory are stored row-major with the column index XOR-swizzled by bit 1 of the
+// row:  (a, b) -> a*8 + (b ^ tile_sw(a)).  A half-warp then reads the DMMA operand fragment
+// (a = lane%4 [+4], b = lane/4) from 16 distinct 8-byte bank pairs; plain row-major puts rows a and
+// a+2 on the same banks (2-way conflict on every operand load of the panel / trailing update:
+// 4.7e9 excess wavefronts per C4 user half-step in profiles/r01_solve_final_ncu.csv).
+__device__ __forceinline__ int tile_sw(int a) { return ((a >> 1) & 1) << 2; }
+// operand-fragment offset: element (lane%4, lane/4); the k+4 half is at +32
+__device__ __forceinline__ int tile_frag_off(int lane) { return (lane & 3) * 8 + ((lane >> 2) ^ tile_sw(lane & 3)); }
+// accumulator-fragment offset (double2): element (lane/4, 2*(lane%4))
+__device__ __forceinline__ int tile_acc_off(int lane) { return (lane >> 2) * 8 + ((2 * (lane & 3)) ^ tile_sw(lane >> 2)); }
+
 // ------------------------------------------------------------------------------------------
 // Gram kernel: partial upper-tile Gram of rows [r0, r1) per CTA (contiguous rows streamed by TMA
 // bulk copies, one per row), then a deterministic reduce
@@ -301,7 +312,7 @@ struct SolveParams {
 
 
 
-// One warp: factor the 8x8 diagonal tile A = U^T U and write W = inv(U) (row-major, upper) to
+// One warp: factor the 8x8 diagonal tile A = U^T U and write W^T = inv(U)^T (swizzled tile) to
 // wtile.  C-fragment layout: lane holds row lane/4, columns 2*(lane%4)+{0,1}; an identity is
 // eliminated alongside.  The elimination is FRACTION-FREE so that the pivot-to-pivot dependency
 // chain is one shuffle + three FP64 ops instead of a reciprocal/rsqrt sequence:
@@ -312,7 +323,7 @@ struct SolveParams {
 // Returns false on a non-positive pivot (reference: dsysv info != 0, qmf/Matrix.cpp:94).
 __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile, double* scratch, int lane) {
   const int r = lane >> 2, q = lane & 3;
-  const double2 a = *reinterpret_cast<const double2*>(tile + lane * 2);
+  const double2 a = *reinterpret_cast<const double2*>(tile + tile_acc_off(lane));
   double a0 = a.x, a1 = a.y;
   double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
   double S = 1.0, prS = 1.0;
@@ -353,8 +364,8 @@ __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile,
     if (r == 7) prS = p7 * S;
   }
   const double g = rsqrt(prS);
-  wtile[(2 * q) * 8 + r] = e0 * g;
-  wtile[(2 * q + 1) * 8 + r] = e1 * g;
+  // stored TRANSPOSED (wtile(r, c) = inv(U)[c][r]) so that this is one conflict-free 16-byte store
+  *reinterpret_cast<double2*>(wtile + tile_acc_off(lane)) = make_double2(e0 * g, e1 * g);
   return ok;
 }
 
@@ -494,7 +505,7 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
       if (c0 == r) v0 = gi < k ? v0 + lambda : 1.0;
       if (c0 + 1 == r) v1 = gi < k ? v1 + lambda : 1.0;
     }
-    *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(I, J)) * 64 + lane * 2) = make_double2(v0, v1);
+    *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(I, J)) * 64 + tile_acc_off(lane)) = make_double2(v0, v1);
   }
 }
 
@@ -546,7 +557,9 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
   int it = 0;
   __syncthreads();  // barriers initialised, first row slot visible
 
-  const int fo = (lane & 3) * 8 + (lane >> 2);  // fragment offset inside a tile (see tile_mma_tn)
+  const int fo = tile_frag_off(lane);                        // operand-fragment offset inside a tile
+  const int fw = (lane >> 2) * 8 + ((lane & 3) ^ tile_sw(lane >> 2));  // same for the transposed W tiles; k+4 half at fw ^ 4
+  const int co = tile_acc_off(lane);                         // accumulator-fragment offset
   for (;;) {
     const volatile RowSlot* cs = slots + (it & 1);
     if (cs->row < 0) break;
@@ -573,10 +586,13 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
 #pragma unroll
       for (int w = 0; w < SM::NWARPS; ++w) b += bhalf[w * SM::KP + tid];
       bcopy[tid] = b;
-      double* bt = tiles + size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8;
-      bt[0] = b;
+      const int br = tid & 7;
+      double* bt = tiles + size_t(SM::tidx(tid >> 3, NT)) * 64 + br * 8;
 #pragma unroll
-      for (int c = 1; c < 8; ++c) bt[c] = 0.0;
+      for (int j = 0; j < 4; ++j) {  // rotated start pair: the 8 rows of a tile hit 8 different 16-byte bank groups
+        const int x2 = 2 * ((j + (br >> 1)) & 3);
+        *reinterpret_cast<double2*>(bt + x2) = make_double2(x2 == tile_sw(br) ? b : 0.0, 0.0);
+      }
     }
     // ---- blocked Cholesky, panel width 8; forward substitution rides along in column NT ------
     bool ok = true;
@@ -592,14 +608,14 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       QMFB_ACC(4, ts0, ts1);
       // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+1 .. NT
       {
-        const double w0 = wt[I * 64 + fo], w1 = wt[I * 64 + fo + 32];
+        const double w0 = wt[I * 64 + fw], w1 = wt[I * 64 + (fw ^ 4)];
         for (int J = I + 1 + warp; J <= NT; J += SM::NWARPS) {
           double* t = tiles + size_t(SM::tidx(I, J)) * 64;
           double c[2] = {0.0, 0.0};
           dmma(c, w0, t[fo]);
           dmma(c, w1, t[fo + 32]);
           __syncwarp();
-          *reinterpret_cast<double2*>(t + lane * 2) = make_double2(c[0], c[1]);
+          *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
         }
       }
       QMFB_T(ts2);
@@ -619,12 +635,12 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       if (SM::NWARPS == 1 || warp == dwarp) {
         double* t = tiles + size_t(tstart) * 64;
         const double* u = urow + 64;
-        double2 cv = *reinterpret_cast<double2*>(t + lane * 2);
+        double2 cv = *reinterpret_cast<double2*>(t + co);
         double c[2] = {cv.x, cv.y};
         const double u0 = u[fo], u1 = u[fo + 32];
         dmma(c, -u0, u0);
         dmma(c, -u1, u1);
-        *reinterpret_cast<double2*>(t + lane * 2) = make_double2(c[0], c[1]);
+        *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
         __syncwarp();
         QMFB_T(tf0);
         ok = factor_diag_tile(t, wt + (I + 1) * 64, fscratch, lane) && ok;
@@ -650,7 +666,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
               }
               const double* ta = urow + (J1 - I) * 64;
               const double* tb = urow + (J1 + off - I) * 64;
-              const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(ti) * 64 + lane * 2);
+              const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(ti) * 64 + co);
               c[q][0] = cv.x; c[q][1] = cv.y;
               ua[q][0] = -ta[fo]; ua[q][1] = -ta[fo + 32];
               ub[q][0] = tb[fo]; ub[q][1] = tb[fo + 32];
@@ -667,7 +683,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int ti = e + q * nw;
-            if (ti < SM::NTILE) *reinterpret_cast<double2*>(tiles + size_t(ti) * 64 + lane * 2) = make_double2(c[q][0], c[q][1]);
+            if (ti < SM::NTILE) *reinterpret_cast<double2*>(tiles + size_t(ti) * 64 + co) = make_double2(c[q][0], c[q][1]);
           }
         }
       }
@@ -681,18 +697,19 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
     __syncthreads();
     double r = 0.0;
     if (tid < SM::KP) {
-      r = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8];
+      r = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
       if ((tid >> 3) == NT - 1) rvec[tid & 7] = r;
     }
     for (int J = NT - 1; J >= 0; --J) {
       __syncthreads();
       if ((tid >> 3) == J) {  // x_J = W_J * r_J
-        const double* w = wt + J * 64 + (tid & 7) * 8;
+        const double* w = wt + J * 64;  // transposed: inv(U_JJ)[row][c] = w(c, row)
+        const int row = tid & 7;
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
-          s0 += w[c] * rvec[c];
-          s1 += w[c + 1] * rvec[c + 1];
+          s0 += w[c * 8 + (row ^ tile_sw(c))] * rvec[c];
+          s1 += w[(c + 1) * 8 + (row ^ tile_sw(c + 1))] * rvec[c + 1];
         }
         xvec[tid] = s0 + s1;
       }
@@ -704,8 +721,8 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
-          const int cr = (c + 2 * (tid & 3)) & 7;  // rotate the start column to spread banks
-          const double2 uv = *reinterpret_cast<const double2*>(u + cr);
+          const int cr = (c + 2 * ((tid >> 1) & 3)) & 7;  // rotate the start pair by row/2: 8 rows -> 8 bank groups
+          const double2 uv = *reinterpret_cast<const double2*>(u + (cr ^ tile_sw(tid & 7)));
           s0 += uv.x * x[cr];
           s1 += uv.y * x[cr + 1];
         }
@@ -720,7 +737,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
     if (warp == 0) {
       double part = 0.0;
       for (int i = lane; i < prm.k; i += 32) {
-        const double z = tiles[size_t(SM::tidx(i >> 3, NT)) * 64 + (i & 7) * 8];
+        const double z = tiles[size_t(SM::tidx(i >> 3, NT)) * 64 + (i & 7) * 8 + tile_sw(i & 7)];
         const double x = xvec[i];
         part += z * z - prm.lambda * x * x - 2.0 * x * bcopy[i];
       }
