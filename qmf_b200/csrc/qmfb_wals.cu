@@ -62,9 +62,9 @@ extern "C" {
 
 #ifdef QMFB_PROFILE_PHASES
 // debug build only (not part of include/qmf_b200.h): read and reset the phase cycle counters
-int qmfb_debug_phase_cycles(unsigned long long* out16) {
-  QMFB_CUDA(cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(unsigned long long) * 16));
-  unsigned long long zero[16] = {0};
+int qmfb_debug_phase_cycles(unsigned long long* out24) {
+  QMFB_CUDA(cudaMemcpyFromSymbol(out24, g_phase_cycles, sizeof(unsigned long long) * 24));
+  unsigned long long zero[24] = {0};
   QMFB_CUDA(cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)));
   return QMFB_OK;
 }

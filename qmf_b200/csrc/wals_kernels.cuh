@@ -36,6 +36,7 @@
 namespace qmfb {
 
 constexpr int kChunk = 16;   // gathered rows per pipeline stage
+constexpr int kTU = 4;       // trailing-update tiles in flight per warp
 constexpr int kStages = 4;   // ring depth
 
 // ------------------------------------------------------------------------------------------
@@ -128,8 +129,8 @@ struct WalsSmem {
   static constexpr size_t kOffX = kOffB + size_t(KP) * 8;                    // x (KP)
   static constexpr size_t kOffR = kOffX + size_t(KP) * 8;                    // back-substitution rhs (8)
   static constexpr size_t kOffFs = kOffR + 64;                               // pivot-row broadcast scratch (16 doubles)
-  static constexpr size_t kOffBh = kOffFs + 128;                             // per-warp partial b (NWARPS*KP) + csum (NWARPS)
-  static constexpr size_t kOffBar = kOffBh + size_t(NWARPS) * (KP + 1) * 8;  // full[kStages], empty[kStages]
+  static constexpr size_t kOffBh = kOffFs + 128;                             // per-warp partial sum of (1 + alpha r) (NWARPS, padded to 8)
+  static constexpr size_t kOffBar = kOffBh + 64;                             // full[kStages], empty[kStages]
   static constexpr size_t kOffRow = kOffBar + size_t(kStages) * 16;          // 2 row slots x 32 bytes
   static constexpr size_t kBytes = kOffRow + 64;
 
@@ -145,14 +146,23 @@ struct WalsSmem {
 // ------------------------------------------------------------------------------------------
 // Row-pair tiling: warp W owns tile rows I0 = W (NT-W tiles) and I1 = NT-1-W (W+1 tiles);
 // acc[0..N0) are row I0, acc[N0..NT+1) row I1.
-template <int NT, int W>
-__device__ __forceinline__ void chunk_mma_rows(double (&acc)[NT + 1][2], const double* sb, const double* wt, int lane) {
+// With WITH_B the right-hand side rides along on the tensor pipe: acc[NT+1] / acc[NT+2] are the b
+// column tiles of tile rows I0 / I1,  b(8I+m) = sum_s y_s(8I+m) * wb_s, i.e. the operand fragment
+// already in registers times a B fragment that holds wb_s in column 0 and zeros elsewhere - exactly
+// the (column 0 = b) tile the blocked Cholesky carries as column NT.
+template <int NT, int W, bool WITH_B>
+__device__ __forceinline__ void chunk_mma_rows(double (&acc)[NT + 3][2], const double* sb, const double* wt, int lane) {
   using SM = WalsSmem<NT>;
   constexpr int I0 = W, I1 = NT - 1 - W, N0 = NT - I0, N1 = NT - I1, D = I1 - I0;
 #pragma unroll
   for (int s0 = 0; s0 < kChunk; s0 += 4) {
     const double* p = sb + (s0 + (lane & 3)) * SM::LD + (lane >> 2) + 8 * I0;
     const double wa = wt[s0 + (lane & 3)];
+    double wbf = 0.0;
+    if constexpr (WITH_B) {
+      const double wb = wt[kChunk + s0 + (lane & 3)];
+      wbf = (lane >> 2) == 0 ? wb : 0.0;
+    }
     double bf[N0];
 #pragma unroll
     for (int j = 0; j < N0; ++j) bf[j] = p[8 * j];
@@ -160,24 +170,21 @@ __device__ __forceinline__ void chunk_mma_rows(double (&acc)[NT + 1][2], const d
     const double a1 = bf[D] * wa;
 #pragma unroll
     for (int j = 0; j < N0; ++j) dmma(acc[j], a0, bf[j]);
+    if constexpr (WITH_B) dmma(acc[NT + 1], bf[0], wbf);
 #pragma unroll
     for (int j = 0; j < N1; ++j) dmma(acc[N0 + j], a1, bf[D + j]);
+    if constexpr (WITH_B) dmma(acc[NT + 2], bf[D], wbf);
   }
 }
 
-template <int NT, int W>
-__device__ __forceinline__ void chunk_mma(double (&acc)[NT + 1][2], const double* sb, const double* wt, int lane) {
-  chunk_mma_rows<NT, W>(acc, sb, wt, lane);
-}
-
-template <int NT, int W>
-__device__ __forceinline__ void chunk_mma_dispatch(int warp, double (&acc)[NT + 1][2], const double* sb,
+template <int NT, int W, bool WITH_B>
+__device__ __forceinline__ void chunk_mma_dispatch(int warp, double (&acc)[NT + 3][2], const double* sb,
                                                    const double* wt, int lane) {
   if constexpr (W < NT / 2) {
     if (warp == W) {
-      chunk_mma<NT, W>(acc, sb, wt, lane);
+      chunk_mma_rows<NT, W, WITH_B>(acc, sb, wt, lane);
     } else {
-      chunk_mma_dispatch<NT, W + 1>(warp, acc, sb, wt, lane);
+      chunk_mma_dispatch<NT, W + 1, WITH_B>(warp, acc, sb, wt, lane);
     }
   }
 }
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(co
   double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* empty = full + kStages;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
@@ -246,9 +253,9 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(co
     if (lane < kChunk) bulk_g2s(stagebuf + (size_t(st) * kChunk + lane) * SM::LD, Y + (valid ? p : r0) * ldy, SM::KP * 8, &full[st]);
   };
 
-  double acc[NT + 1][2];
+  double acc[NT + 3][2];
 #pragma unroll
-  for (int t = 0; t <= NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+  for (int t = 0; t < NT + 3; ++t) acc[t][0] = acc[t][1] = 0.0;
   if (warp == 0) {
     for (int c = 0; c < nch && c < kStages - 1; ++c) issue(c);
   }
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(co
     const uint32_t st = c % kStages;
     if (warp == 0 && c + kStages - 1 < nch) issue(c + kStages - 1);
     mbar_wait(&full[st], (c / kStages) & 1u);
-    chunk_mma_dispatch<NT, 0>(warp, acc, stagebuf + size_t(st) * kChunk * SM::LD, wts + st * 2 * kChunk, lane);
+    chunk_mma_dispatch<NT, 0, false>(warp, acc, stagebuf + size_t(st) * kChunk * SM::LD, wts + st * 2 * kChunk, lane);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
   }
@@ -373,7 +380,7 @@ __device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile,
 // debug build only: thread 0 of every CTA accumulates clock64() deltas per phase into
 // g_phase_cycles[phase] (build, tile store, factor (warp 0), panel, trailing/wait, back
 // substitution, tail) and g_phase_cycles[15] counts rows
-__device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_phase_cycles[24];
 __device__ int g_debug_flags;  // bit 0: skip the trailing updates of the non-diagonal warps (timing experiments only)
 #define QMFB_T(var) const long long var = clock64()
 #define QMFB_ACC(idx, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[idx], (unsigned long long)((b) - (a))); } while (0)
@@ -407,11 +414,11 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
   double* bpart = reinterpret_cast<double*>(smem + SM::kOffBh);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* empty = full + kStages;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   constexpr int PPR = SM::KP / 2;             // 16-byte pieces per gathered row
   constexpr int NCOPY = kChunk * PPR / 32;    // cp.async per lane per chunk
-  constexpr int NBC = SM::KP / 32;            // b columns per lane
   constexpr int kAhead = kStages - 2;         // chunks in flight beyond the one being consumed
+  QMFB_T(tq0);
   const int nch = int((p1 - p0 + kChunk - 1) / kChunk);
   const uint32_t lim = base + uint32_t(nch);  // the ring is reused as tile storage: no cross-row prefetch
 
@@ -420,9 +427,7 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
   int32_t pcol = 0;   // lanes < kChunk: column of row `lane` of chunk `mine`
   double pval = 0.0;
   bool pvalid = false;
-  double csum = 0.0, bcol[NBC];
-#pragma unroll
-  for (int j = 0; j < NBC; ++j) bcol[j] = 0.0;
+  double csum = 0.0;
   auto prefetch_idx = [&]() {
     const int64_t p = p0 + int64_t(mine - base) * kChunk + lane;
     pvalid = lane < kChunk && mine < lim && p < p1;
@@ -452,7 +457,9 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
   prefetch_idx();
   if (mine < lim && mine < base + kAhead) issue_mine();  // prologue: the first kAhead chunks of the row
 
-  double acc[NT + 1][2];
+  QMFB_T(tq1);
+  double acc[NT + 3][2];
+  acc[NT + 1][0] = acc[NT + 1][1] = acc[NT + 2][0] = acc[NT + 2][1] = 0.0;  // b column tiles of this warp's two tile rows
 #pragma unroll
   for (int t = 0; t <= NT; ++t) {  // accumulators start from the Gram tiles
     int I, J;
@@ -461,25 +468,20 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
     acc[t][0] = g.x;
     acc[t][1] = g.y;
   }
+  QMFB_T(tq2);
   for (int c = 0; c < nch; ++c) {
     const uint32_t gc = base + c, st = gc % kStages;
     // the stage refilled here was consumed TWO chunks ago: its empty barrier completed long ago
+    QMFB_T(tb0);
     if (mine == gc + kAhead && mine < lim) issue_mine();
     QMFB_T(tb1);
+    QMFB_ACC(11, tb0, tb1);
     mbar_wait(&full[st], (gc / kStages) & 1u);
     QMFB_T(tb2);
     const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
     const double* w8 = wts + st * 2 * kChunk;
-    chunk_mma_dispatch<NT, 0>(warp, acc, sb, w8, lane);
+    chunk_mma_dispatch<NT, 0, true>(warp, acc, sb, w8, lane);
     QMFB_T(tb3);
-    if (int(gc % SM::NWARPS) == warp) {  // this chunk's b accumulation is ours
-#pragma unroll 4
-      for (int s = 0; s < kChunk; ++s) {
-        const double w = w8[kChunk + s];
-#pragma unroll
-        for (int j = 0; j < NBC; ++j) bcol[j] += w * sb[s * SM::LD + lane + 32 * j];
-      }
-    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
     QMFB_T(tb4);
@@ -487,12 +489,13 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
     QMFB_ACC(13, tb2, tb3);
     QMFB_ACC(14, tb3, tb4);
   }
+  QMFB_T(tq3);
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-#pragma unroll
-  for (int j = 0; j < NBC; ++j) bpart[warp * SM::KP + lane + 32 * j] = bcol[j];
-  if (lane == 0) bpart[SM::NWARPS * SM::KP + warp] = csum;
+  if (lane == 0) bpart[warp] = csum;
+  QMFB_T(tq4);
   __syncthreads();  // every warp is done reading the ring before the tiles overwrite it
+  QMFB_T(tq5);
   // tiles to shared memory: A(i,i) += lambda (WALSEngine.cpp:290-292), unit pivot on padding
   const int r = lane >> 2, c0 = 2 * (lane & 3);
 #pragma unroll
@@ -507,6 +510,178 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
     }
     *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(I, J)) * 64 + tile_acc_off(lane)) = make_double2(v0, v1);
   }
+  *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(warp, NT)) * 64 + tile_acc_off(lane)) = make_double2(acc[NT + 1][0], acc[NT + 1][1]);
+  *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(NT - 1 - warp, NT)) * 64 + tile_acc_off(lane)) = make_double2(acc[NT + 2][0], acc[NT + 2][1]);
+  QMFB_T(tq6);
+  QMFB_ACC(16, tq0, tq1);
+  QMFB_ACC(17, tq1, tq2);
+  QMFB_ACC(18, tq2, tq3);
+  QMFB_ACC(19, tq3, tq4);
+  QMFB_ACC(20, tq4, tq5);
+  QMFB_ACC(21, tq5, tq6);
+}
+
+// Factor + solve phase of one row, entirely in shared memory: blocked right-looking Cholesky of the
+// upper tiles (panel width 8, b as tile column NT so that the forward substitution rides along),
+// then the back substitution; leaves x in xvec, z in the b tiles, b in bcopy.  Deliberately its own
+// (non-inlined) function: its register allocation is then independent of the build phase, whose
+// 34+ accumulator registers otherwise push the operand fragments of the trailing update into local
+// memory (3 STL.64 + 3 LDL.64 per four tiles in profiles/r01_solve_final_ncu.csv).
+// Returns false on a non-positive pivot.
+template <int NT>
+__device__ __noinline__ bool solve_row(unsigned char* smem) {
+  using SM = WalsSmem<NT>;
+  double* tiles = reinterpret_cast<double*>(smem + SM::kOffTiles);
+  double* wt = reinterpret_cast<double*>(smem + SM::kOffW);
+  double* bcopy = reinterpret_cast<double*>(smem + SM::kOffB);
+  double* xvec = reinterpret_cast<double*>(smem + SM::kOffX);
+  double* rvec = reinterpret_cast<double*>(smem + SM::kOffR);
+  double* fscratch = reinterpret_cast<double*>(smem + SM::kOffFs);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int fo = tile_frag_off(lane);                        // operand-fragment offset inside a tile
+  const int fw = (lane >> 2) * 8 + ((lane & 3) ^ tile_sw(lane >> 2));  // same for the transposed W tiles; k+4 half at fw ^ 4
+  const int co = tile_acc_off(lane);                         // accumulator-fragment offset
+  QMFB_T(tp1);
+  // keep a copy of b (column 0 of the b tiles) for the loss before the factorisation overwrites it with z
+  if (tid < SM::KP) bcopy[tid] = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
+  // ---- blocked Cholesky, panel width 8; forward substitution rides along in column NT ------
+  bool ok = true;
+  QMFB_T(tp2);
+  QMFB_ACC(1, tp1, tp2);
+  if (warp == 0) ok = factor_diag_tile(tiles + size_t(SM::tidx(0, 0)) * 64, wt, fscratch, lane);
+  QMFB_T(tp3);
+  QMFB_ACC(2, tp2, tp3);
+  for (int I = 0; I < NT; ++I) {
+    QMFB_T(ts0);
+    __syncthreads();  // W_I ready, row I of tiles final up to panel I-1
+    QMFB_T(ts1);
+    QMFB_ACC(4, ts0, ts1);
+    // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+1 .. NT
+    {
+      const double w0 = wt[I * 64 + fw], w1 = wt[I * 64 + (fw ^ 4)];
+      for (int J = I + 1 + warp; J <= NT; J += SM::NWARPS) {
+        double* t = tiles + size_t(SM::tidx(I, J)) * 64;
+        double c[2] = {0.0, 0.0};
+        dmma(c, w0, t[fo]);
+        dmma(c, w1, t[fo + 32]);
+        __syncwarp();
+        *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
+      }
+    }
+    QMFB_T(ts2);
+    QMFB_ACC(3, ts1, ts2);
+    if (I == NT - 1) break;
+    __syncthreads();
+    QMFB_T(ts3);
+    QMFB_ACC(5, ts2, ts3);
+    // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT.
+    //     One warp updates the next diagonal tile first and factors it right away (look-ahead)
+    //     while the other warps sweep the rest, four independent tiles at a time.
+    const int tstart = SM::tidx(I + 1, I + 1);
+    const double* urow = tiles + size_t(SM::tidx(I, I)) * 64;  // tile (I, J) = urow + (J - I) * 64
+    constexpr int dwarp = 0;
+    const int nw = SM::NWARPS > 1 ? SM::NWARPS - 1 : 1;
+    const int wslot = SM::NWARPS > 1 ? warp - 1 : 0;
+    if (SM::NWARPS == 1 || warp == dwarp) {
+      double* t = tiles + size_t(tstart) * 64;
+      const double* u = urow + 64;
+      double2 cv = *reinterpret_cast<double2*>(t + co);
+      double c[2] = {cv.x, cv.y};
+      const double u0 = u[fo], u1 = u[fo + 32];
+      dmma(c, -u0, u0);
+      dmma(c, -u1, u1);
+      *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
+      __syncwarp();
+      QMFB_T(tf0);
+      ok = factor_diag_tile(t, wt + (I + 1) * 64, fscratch, lane) && ok;
+      QMFB_T(tf1);
+      QMFB_ACC(2, tf0, tf1);
+      QMFB_ACC(6, ts3, tf0);
+    }
+#ifdef QMFB_PROFILE_PHASES
+    if ((g_debug_flags & 1) == 0)
+#endif
+    if (SM::NWARPS == 1 || warp != dwarp) {
+      // flat enumeration of the trailing tiles (contiguous in storage); (J1, J2) decoded incrementally
+      int J1 = I + 1, off = 1 + wslot;  // position `off` inside row J1 (row J1 has NT - J1 + 1 tiles)
+      for (int e = tstart + 1 + wslot; e < SM::NTILE; e += kTU * nw) {
+        // straight-line body: out-of-range slots of the last sweep recompute a valid tile and skip the store
+        double c[kTU][2], ua[kTU][2], ub[kTU][2];
+#pragma unroll
+        for (int q = 0; q < kTU; ++q) {
+          const int ti = e + q * nw;
+          const bool v = ti < SM::NTILE;
+          if (v) {
+            while (off >= NT - J1 + 1) {
+              off -= NT - J1 + 1;
+              ++J1;
+            }
+          }
+          const double* ta = urow + (v ? J1 - I : 1) * 64;
+          const double* tb = urow + (v ? J1 + off - I : 1) * 64;
+          const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(v ? ti : tstart) * 64 + co);
+          c[q][0] = cv.x; c[q][1] = cv.y;
+          ua[q][0] = -ta[fo]; ua[q][1] = -ta[fo + 32];
+          ub[q][0] = tb[fo]; ub[q][1] = tb[fo + 32];
+          off += nw;
+        }
+#pragma unroll
+        for (int q = 0; q < kTU; ++q) {
+          dmma(c[q], ua[q][0], ub[q][0]);
+          dmma(c[q], ua[q][1], ub[q][1]);
+        }
+#pragma unroll
+        for (int q = 0; q < kTU; ++q) {
+          const int ti = e + q * nw;
+          if (ti < SM::NTILE) *reinterpret_cast<double2*>(tiles + size_t(ti) * 64 + co) = make_double2(c[q][0], c[q][1]);
+        }
+      }
+    }
+  }
+  QMFB_T(tp4);
+  QMFB_ACC(7, tp3, tp4);
+
+  // ---- back substitution U x = z: thread t < KP keeps r_t in a register; per block step one
+  //      8x8 mat-vec by inv(U_JJ) and one rank-8 update of the rows above -----------------------
+  __syncthreads();
+  double r = 0.0;
+  if (tid < SM::KP) {
+    r = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
+    if ((tid >> 3) == NT - 1) rvec[tid & 7] = r;
+  }
+  for (int J = NT - 1; J >= 0; --J) {
+    __syncthreads();
+    if ((tid >> 3) == J) {  // x_J = W_J * r_J
+      const double* w = wt + J * 64;  // transposed: inv(U_JJ)[row][c] = w(c, row)
+      const int row = tid & 7;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        s0 += w[c * 8 + (row ^ tile_sw(c))] * rvec[c];
+        s1 += w[(c + 1) * 8 + (row ^ tile_sw(c + 1))] * rvec[c + 1];
+      }
+      xvec[tid] = s0 + s1;
+    }
+    if (J == 0) break;
+    __syncthreads();
+    if (tid < 8 * J) {  // r_t -= U[t][8J .. 8J+7] . x_J
+      const double* u = tiles + size_t(SM::tidx(tid >> 3, J)) * 64 + (tid & 7) * 8;
+      const double* x = xvec + 8 * J;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        const int cr = (c + 2 * ((tid >> 1) & 3)) & 7;  // rotate the start pair by row/2: 8 rows -> 8 bank groups
+        const double2 uv = *reinterpret_cast<const double2*>(u + (cr ^ tile_sw(tid & 7)));
+        s0 += uv.x * x[cr];
+        s1 += uv.y * x[cr + 1];
+      }
+      r -= s0 + s1;
+      if ((tid >> 3) == J - 1) rvec[tid & 7] = r;
+    }
+  }
+  QMFB_T(tp5);
+  QMFB_ACC(8, tp4, tp5);
+  return ok;
 }
 
 template <int NT>
@@ -524,7 +699,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
   double* bhalf = reinterpret_cast<double*>(smem + SM::kOffBh);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* empty = full + kStages;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, tid = threadIdx.x;
   constexpr int TPR = SM::KP / 2;  // threads per gathered row (16 bytes each); 4 rows per pass
 
   if (tid == 0) {
@@ -557,9 +732,6 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
   int it = 0;
   __syncthreads();  // barriers initialised, first row slot visible
 
-  const int fo = tile_frag_off(lane);                        // operand-fragment offset inside a tile
-  const int fw = (lane >> 2) * 8 + ((lane & 3) ^ tile_sw(lane >> 2));  // same for the transposed W tiles; k+4 half at fw ^ 4
-  const int co = tile_acc_off(lane);                         // accumulator-fragment offset
   for (;;) {
     const volatile RowSlot* cs = slots + (it & 1);
     if (cs->row < 0) break;
@@ -580,159 +752,9 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       np1 = __ldg(prm.row_ptr + nrow + 1);
     }
     __syncthreads();
-    // b = sum of the per-warp partial sums; b column tiles (column 0 = b, other columns 0); keep a copy
-    if (tid < SM::KP) {
-      double b = 0.0;
-#pragma unroll
-      for (int w = 0; w < SM::NWARPS; ++w) b += bhalf[w * SM::KP + tid];
-      bcopy[tid] = b;
-      const int br = tid & 7;
-      double* bt = tiles + size_t(SM::tidx(tid >> 3, NT)) * 64 + br * 8;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {  // rotated start pair: the 8 rows of a tile hit 8 different 16-byte bank groups
-        const int x2 = 2 * ((j + (br >> 1)) & 3);
-        *reinterpret_cast<double2*>(bt + x2) = make_double2(x2 == tile_sw(br) ? b : 0.0, 0.0);
-      }
-    }
-    // ---- blocked Cholesky, panel width 8; forward substitution rides along in column NT ------
-    bool ok = true;
-    QMFB_T(tp2);
-    QMFB_ACC(1, tp1, tp2);
-    if (warp == 0) ok = factor_diag_tile(tiles + size_t(SM::tidx(0, 0)) * 64, wt, fscratch, lane);
-    QMFB_T(tp3);
-    QMFB_ACC(2, tp2, tp3);
-    for (int I = 0; I < NT; ++I) {
-      QMFB_T(ts0);
-      __syncthreads();  // W_I ready, row I of tiles final up to panel I-1
-      QMFB_T(ts1);
-      QMFB_ACC(4, ts0, ts1);
-      // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+1 .. NT
-      {
-        const double w0 = wt[I * 64 + fw], w1 = wt[I * 64 + (fw ^ 4)];
-        for (int J = I + 1 + warp; J <= NT; J += SM::NWARPS) {
-          double* t = tiles + size_t(SM::tidx(I, J)) * 64;
-          double c[2] = {0.0, 0.0};
-          dmma(c, w0, t[fo]);
-          dmma(c, w1, t[fo + 32]);
-          __syncwarp();
-          *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
-        }
-      }
-      QMFB_T(ts2);
-      QMFB_ACC(3, ts1, ts2);
-      if (I == NT - 1) break;
-      __syncthreads();
-      QMFB_T(ts3);
-      QMFB_ACC(5, ts2, ts3);
-      // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT.
-      //     One warp updates the next diagonal tile first and factors it right away (look-ahead)
-      //     while the other warps sweep the rest, four independent tiles at a time.
-      const int tstart = SM::tidx(I + 1, I + 1);
-      const double* urow = tiles + size_t(SM::tidx(I, I)) * 64;  // tile (I, J) = urow + (J - I) * 64
-      constexpr int dwarp = 0;
-      const int nw = SM::NWARPS > 1 ? SM::NWARPS - 1 : 1;
-      const int wslot = SM::NWARPS > 1 ? warp - 1 : 0;
-      if (SM::NWARPS == 1 || warp == dwarp) {
-        double* t = tiles + size_t(tstart) * 64;
-        const double* u = urow + 64;
-        double2 cv = *reinterpret_cast<double2*>(t + co);
-        double c[2] = {cv.x, cv.y};
-        const double u0 = u[fo], u1 = u[fo + 32];
-        dmma(c, -u0, u0);
-        dmma(c, -u1, u1);
-        *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
-        __syncwarp();
-        QMFB_T(tf0);
-        ok = factor_diag_tile(t, wt + (I + 1) * 64, fscratch, lane) && ok;
-        QMFB_T(tf1);
-        QMFB_ACC(2, tf0, tf1);
-        QMFB_ACC(6, ts3, tf0);
-      }
-#ifdef QMFB_PROFILE_PHASES
-      if ((g_debug_flags & 1) == 0)
-#endif
-      if (SM::NWARPS == 1 || warp != dwarp) {
-        // flat enumeration of the trailing tiles (contiguous in storage); (J1, J2) decoded incrementally
-        int J1 = I + 1, off = 1 + wslot;  // position `off` inside row J1 (row J1 has NT - J1 + 1 tiles)
-        for (int e = tstart + 1 + wslot; e < SM::NTILE; e += 4 * nw) {
-          double c[4][2], ua[4][2], ub[4][2];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int ti = e + q * nw;
-            if (ti < SM::NTILE) {
-              while (off >= NT - J1 + 1) {
-                off -= NT - J1 + 1;
-                ++J1;
-              }
-              const double* ta = urow + (J1 - I) * 64;
-              const double* tb = urow + (J1 + off - I) * 64;
-              const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(ti) * 64 + co);
-              c[q][0] = cv.x; c[q][1] = cv.y;
-              ua[q][0] = -ta[fo]; ua[q][1] = -ta[fo + 32];
-              ub[q][0] = tb[fo]; ub[q][1] = tb[fo + 32];
-              off += nw;
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (e + q * nw < SM::NTILE) {
-              dmma(c[q], ua[q][0], ub[q][0]);
-              dmma(c[q], ua[q][1], ub[q][1]);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int ti = e + q * nw;
-            if (ti < SM::NTILE) *reinterpret_cast<double2*>(tiles + size_t(ti) * 64 + co) = make_double2(c[q][0], c[q][1]);
-          }
-        }
-      }
-    }
-    if (!ok && lane == 0) *prm.error = 1;
-    QMFB_T(tp4);
-    QMFB_ACC(7, tp3, tp4);
-
-    // ---- back substitution U x = z: thread t < KP keeps r_t in a register; per block step one
-    //      8x8 mat-vec by inv(U_JJ) and one rank-8 update of the rows above -----------------------
-    __syncthreads();
-    double r = 0.0;
-    if (tid < SM::KP) {
-      r = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
-      if ((tid >> 3) == NT - 1) rvec[tid & 7] = r;
-    }
-    for (int J = NT - 1; J >= 0; --J) {
-      __syncthreads();
-      if ((tid >> 3) == J) {  // x_J = W_J * r_J
-        const double* w = wt + J * 64;  // transposed: inv(U_JJ)[row][c] = w(c, row)
-        const int row = tid & 7;
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          s0 += w[c * 8 + (row ^ tile_sw(c))] * rvec[c];
-          s1 += w[(c + 1) * 8 + (row ^ tile_sw(c + 1))] * rvec[c + 1];
-        }
-        xvec[tid] = s0 + s1;
-      }
-      if (J == 0) break;
-      __syncthreads();
-      if (tid < 8 * J) {  // r_t -= U[t][8J .. 8J+7] . x_J
-        const double* u = tiles + size_t(SM::tidx(tid >> 3, J)) * 64 + (tid & 7) * 8;
-        const double* x = xvec + 8 * J;
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          const int cr = (c + 2 * ((tid >> 1) & 3)) & 7;  // rotate the start pair by row/2: 8 rows -> 8 bank groups
-          const double2 uv = *reinterpret_cast<const double2*>(u + (cr ^ tile_sw(tid & 7)));
-          s0 += uv.x * x[cr];
-          s1 += uv.y * x[cr + 1];
-        }
-        r -= s0 + s1;
-        if ((tid >> 3) == J - 1) rvec[tid & 7] = r;
-      }
-    }
+    if (!solve_row<NT>(smem) && lane == 0) *prm.error = 1;
     __syncthreads();
     QMFB_T(tp5);
-    QMFB_ACC(8, tp4, tp5);
     // ---- loss term: c + x^T B x - 2 x^T b with x^T B x = z^T z - lambda x^T x (WALSEngine.cpp:295-304)
     if (warp == 0) {
       double part = 0.0;
@@ -741,7 +763,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
         const double x = xvec[i];
         part += z * z - prm.lambda * x * x - 2.0 * x * bcopy[i];
       }
-      if (lane < SM::NWARPS) part += bhalf[SM::NWARPS * SM::KP + lane];  // sum_s (1 + alpha r_s), WALSEngine.cpp:286
+      if (lane < SM::NWARPS) part += bhalf[lane];  // sum_s (1 + alpha r_s), WALSEngine.cpp:286
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
       if (lane == 0) prm.row_loss[cs->row] = part;

@@ -11,7 +11,8 @@ k = 128
 kp = K.padded_k(k)
 names = ["build", "tile store+b", "factor diag (warp0)", "panel (b)", "wait top-of-step", "wait after panel", "diag tile update",
          "cholesky total", "back substitution", "loss/store/next", "row total", "  build: issue_one", "  build: wait full",
-         "  build: chunk_mma", "  build: b-acc + arrive"]
+         "  build: chunk_mma", "  build: b-acc + arrive", "(rows)", "  build: prologue issue", "  build: gram load", "  build: chunk loop",
+         "  build: b partial store", "  build: end barrier", "  build: tile store"]
 K.lib.qmfb_debug_set_flags(int(os.environ.get("EXP_FLAGS", "0")))
 for spec in sys.argv[1:]:
     nrows, nnz_row, ncols = (int(x) for x in spec.split(","))
@@ -28,7 +29,7 @@ for spec in sys.argv[1:]:
     row_loss = torch.zeros(nrows, device=dev, dtype=torch.float64)
     loss = torch.zeros(1, device=dev, dtype=torch.float64)
     scratch = torch.zeros(2, device=dev, dtype=torch.int32)
-    buf = (C.c_ulonglong * 16)()
+    buf = (C.c_ulonglong * 24)()
     K.solve(X, 0, Y, k, row_ptr, col, val, order, gram, 40.0, 0.05, row_loss, loss, scratch)
     torch.cuda.synchronize()
     K.lib.qmfb_debug_phase_cycles(buf)
@@ -38,4 +39,6 @@ for spec in sys.argv[1:]:
     rows = buf[15]
     print("== rows=%d nnz/row=%d ycols=%d  (cycles per row, thread 0 of each CTA; %d rows)" % (nrows, nnz_row, ncols, rows))
     for i, n in enumerate(names):
+        if i == 15:
+            continue
         print("  %-24s %9.0f" % (n, buf[i] / max(rows, 1)))
