@@ -643,15 +643,16 @@ __device__ __noinline__ bool solve_row(unsigned char* smem) {
 
   // ---- back substitution U x = z: thread t < KP keeps r_t in a register; per block step one
   //      8x8 mat-vec by inv(U_JJ) and one rank-8 update of the rows above -----------------------
+  //      ONE block barrier per step: the eight threads of block J live in one warp, so they exchange
+  //      their finished r_J through shared memory under a __syncwarp and go straight on to x_J.
   __syncthreads();
   double r = 0.0;
-  if (tid < SM::KP) {
-    r = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
-    if ((tid >> 3) == NT - 1) rvec[tid & 7] = r;
-  }
+  if (tid < SM::KP) r = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
   for (int J = NT - 1; J >= 0; --J) {
-    __syncthreads();
-    if ((tid >> 3) == J) {  // x_J = W_J * r_J
+    const bool mine = (tid >> 3) == J;
+    if (mine) rvec[tid & 7] = r;
+    __syncwarp();
+    if (mine) {  // x_J = W_J * r_J
       const double* w = wt + J * 64;  // transposed: inv(U_JJ)[row][c] = w(c, row)
       const int row = tid & 7;
       double s0 = 0.0, s1 = 0.0;
@@ -663,7 +664,7 @@ __device__ __noinline__ bool solve_row(unsigned char* smem) {
       xvec[tid] = s0 + s1;
     }
     if (J == 0) break;
-    __syncthreads();
+    __syncthreads();  // x_J visible; also orders this step's rvec reads before the next step's writes
     if (tid < 8 * J) {  // r_t -= U[t][8J .. 8J+7] . x_J
       const double* u = tiles + size_t(SM::tidx(tid >> 3, J)) * 64 + (tid & 7) * 8;
       const double* x = xvec + 8 * J;
@@ -676,7 +677,6 @@ __device__ __noinline__ bool solve_row(unsigned char* smem) {
         s1 += uv.y * x[cr + 1];
       }
       r -= s0 + s1;
-      if ((tid >> 3) == J - 1) rvec[tid & 7] = r;
     }
   }
   QMFB_T(tp5);
