@@ -36,7 +36,11 @@
 namespace qmfb {
 
 constexpr int kChunk = 16;   // gathered rows per pipeline stage
-constexpr int kTU = 4;       // trailing-update tiles in flight per warp
+// trailing-update tiles in flight per warp.  ONE on purpose: the sweep has the whole duration of the
+// diagonal-tile factor to finish, and bursts of DMMAs / shared-memory loads from it delay that factor's
+// critical path on the shared FP64 pipe (4 in flight: 27.3 ms on the user-shaped half of C4, 1: 25.3 ms;
+// tools/exp_user.py)
+constexpr int kTU = 1;
 constexpr int kStages = 4;   // ring depth
 
 // ------------------------------------------------------------------------------------------
@@ -576,7 +580,7 @@ __device__ __noinline__ bool solve_row(unsigned char* smem) {
     QMFB_ACC(5, ts2, ts3);
     // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT.
     //     One warp updates the next diagonal tile first and factors it right away (look-ahead)
-    //     while the other warps sweep the rest, four independent tiles at a time.
+    //     while the other warps sweep the rest (kTU tiles in flight each).
     const int tstart = SM::tidx(I + 1, I + 1);
     const double* urow = tiles + size_t(SM::tidx(I, I)) * 64;  // tile (I, J) = urow + (J - I) * 64
     constexpr int dwarp = 0;
