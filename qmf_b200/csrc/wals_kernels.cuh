@@ -332,10 +332,8 @@ struct SolveParams {
 // exact).  Row r of the true factor is recovered at the end with a single
 // g_r = rsqrt(p_r * S_r):  U[r][c] = a_rc * g_r,  inv(U)[c][r] = e_rc * g_r.
 // Returns false on a non-positive pivot (reference: dsysv info != 0, qmf/Matrix.cpp:94).
-__device__ __noinline__ bool factor_diag_tile(const double* tile, double* wtile, double* scratch, int lane) {
+__device__ __noinline__ bool factor_diag_tile(double a0, double a1, double* wtile, double* scratch, int lane) {
   const int r = lane >> 2, q = lane & 3;
-  const double2 a = *reinterpret_cast<const double2*>(tile + tile_acc_off(lane));
-  double a0 = a.x, a1 = a.y;
   double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
   double S = 1.0, prS = 1.0;
   bool ok = true;
@@ -552,7 +550,10 @@ __device__ __noinline__ bool solve_row(unsigned char* smem) {
   bool ok = true;
   QMFB_T(tp2);
   QMFB_ACC(1, tp1, tp2);
-  if (warp == 0) ok = factor_diag_tile(tiles + size_t(SM::tidx(0, 0)) * 64, wt, fscratch, lane);
+  if (warp == 0) {
+    const double2 a = *reinterpret_cast<const double2*>(tiles + size_t(SM::tidx(0, 0)) * 64 + co);
+    ok = factor_diag_tile(a.x, a.y, wt, fscratch, lane);
+  }
   QMFB_T(tp3);
   QMFB_ACC(2, tp2, tp3);
   for (int I = 0; I < NT; ++I) {
@@ -594,10 +595,8 @@ __device__ __noinline__ bool solve_row(unsigned char* smem) {
       const double u0 = u[fo], u1 = u[fo + 32];
       dmma(c, -u0, u0);
       dmma(c, -u1, u1);
-      *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
-      __syncwarp();
-      QMFB_T(tf0);
-      ok = factor_diag_tile(t, wt + (I + 1) * 64, fscratch, lane) && ok;
+      QMFB_T(tf0);  // the updated tile goes to the factor in registers (same fragment layout); U_II itself is never read again
+      ok = factor_diag_tile(c[0], c[1], wt + (I + 1) * 64, fscratch, lane) && ok;
       QMFB_T(tf1);
       QMFB_ACC(2, tf0, tf1);
       QMFB_ACC(6, ts3, tf0);
