@@ -359,9 +359,10 @@ __device__ __noinline__ bool factor_diag_tile(double a0, double a1, double* wtil
     if (r == j) prS = p * S;
     S *= pn;
     const bool upd = r > j;
-    const double us = -(ur * sc);
-    const double n0 = fma(a0, pn, us * uc.x), n1 = fma(a1, pn, us * uc.y);
-    const double m0 = fma(e0, pn, us * ec.x), m1 = fma(e1, pn, us * ec.y);
+    // a*pn - (ur*sc)*u  ==  (a*p - ur*u) * sc bit for bit (sc is a power of two): the integer
+    // normalisation of p is then off the dependent FP64 chain (product -> fma -> exact scale)
+    const double n0 = fma(a0, p, -(ur * uc.x)) * sc, n1 = fma(a1, p, -(ur * uc.y)) * sc;
+    const double m0 = fma(e0, p, -(ur * ec.x)) * sc, m1 = fma(e1, p, -(ur * ec.y)) * sc;
     a0 = upd ? n0 : a0;
     a1 = upd ? n1 : a1;
     e0 = upd ? m0 : e0;
