@@ -13,7 +13,7 @@
  *                (qmf_b200/host/qmf/...) bind.
  *
  * Device layout: a factor matrix with k factors is stored row-major with row stride
- * KP = qmfb_padded_k(k) doubles (k rounded up to 32/64/96/128), pad columns are zero.
+ * KP = qmfb_padded_k(k) doubles (k rounded up to a multiple of 32, k <= 256), pad columns are zero.
  */
 #ifndef QMF_B200_H
 #define QMF_B200_H
@@ -42,7 +42,7 @@ int qmfb_version(void);
 int qmfb_device_count(void);
 
 /* ---------------------------------------------------------------- layout helpers ---------- */
-int qmfb_padded_k(int k);                 /* KP; negative if k is unsupported (k < 1 or k > 128) */
+int qmfb_padded_k(int k);                 /* KP; negative if k is unsupported (k < 1 or k > 256) */
 int64_t qmfb_gram_packed_len(int k);      /* doubles in the packed upper-tile Gram of KP x KP */
 int64_t qmfb_gram_workspace_len(int k);   /* doubles of scratch qmfb_gram_dev needs */
 

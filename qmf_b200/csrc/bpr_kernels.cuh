@@ -20,7 +20,7 @@
 
 namespace qmfb {
 
-constexpr int kBprMaxPerLane = 4;  // factors per lane: supports nfactors <= 128
+constexpr int kBprMaxPerLane = 8;  // factors per lane: supports nfactors <= 256
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), counter-based: no RNG state in memory ------------------
 struct Philox {

@@ -260,7 +260,11 @@ int qmfb_bpr_epoch(qmfb_bpr_t* h, double lr, double user_lambda, double item_lam
     case 1: bpr_epoch_kernel<1><<<blocks, 256, 0, h->stream>>>(p); break;
     case 2: bpr_epoch_kernel<2><<<blocks, 256, 0, h->stream>>>(p); break;
     case 3: bpr_epoch_kernel<3><<<blocks, 256, 0, h->stream>>>(p); break;
-    default: bpr_epoch_kernel<4><<<blocks, 256, 0, h->stream>>>(p); break;
+    case 4: bpr_epoch_kernel<4><<<blocks, 256, 0, h->stream>>>(p); break;
+    case 5: bpr_epoch_kernel<5><<<blocks, 256, 0, h->stream>>>(p); break;
+    case 6: bpr_epoch_kernel<6><<<blocks, 256, 0, h->stream>>>(p); break;
+    case 7: bpr_epoch_kernel<7><<<blocks, 256, 0, h->stream>>>(p); break;
+    default: bpr_epoch_kernel<8><<<blocks, 256, 0, h->stream>>>(p); break;
   }
   QMFB_CUDA(cudaGetLastError());
   QMFB_CUDA(cudaEventRecord(h->ev[1], h->stream));
@@ -303,7 +307,11 @@ int qmfb_bpr_update_triplets(qmfb_bpr_t* h, const int32_t* u, const int32_t* i, 
     case 1: bpr_replay_kernel<1><<<1, 32, 0, h->stream>>>(p, h->trip, h->trip + n, h->trip + 2 * n, n); break;
     case 2: bpr_replay_kernel<2><<<1, 32, 0, h->stream>>>(p, h->trip, h->trip + n, h->trip + 2 * n, n); break;
     case 3: bpr_replay_kernel<3><<<1, 32, 0, h->stream>>>(p, h->trip, h->trip + n, h->trip + 2 * n, n); break;
-    default: bpr_replay_kernel<4><<<1, 32, 0, h->stream>>>(p, h->trip, h->trip + n, h->trip + 2 * n, n); break;
+    case 4: bpr_replay_kernel<4><<<1, 32, 0, h->stream>>>(p, h->trip, h->trip + n, h->trip + 2 * n, n); break;
+    case 5: bpr_replay_kernel<5><<<1, 32, 0, h->stream>>>(p, h->trip, h->trip + n, h->trip + 2 * n, n); break;
+    case 6: bpr_replay_kernel<6><<<1, 32, 0, h->stream>>>(p, h->trip, h->trip + n, h->trip + 2 * n, n); break;
+    case 7: bpr_replay_kernel<7><<<1, 32, 0, h->stream>>>(p, h->trip, h->trip + n, h->trip + 2 * n, n); break;
+    default: bpr_replay_kernel<8><<<1, 32, 0, h->stream>>>(p, h->trip, h->trip + n, h->trip + 2 * n, n); break;
   }
   QMFB_CUDA(cudaGetLastError());
   h->launches += 1;
@@ -324,7 +332,11 @@ int qmfb_bpr_eval_loss(qmfb_bpr_t* h, const int32_t* u, const int32_t* i, const 
     case 1: bpr_eval_loss_kernel<1><<<blocks, 256, 0, h->stream>>>(h->F[0], h->F[1], h->bias, h->k, h->trip, h->trip + n, h->trip + 2 * n, n, h->partial); break;
     case 2: bpr_eval_loss_kernel<2><<<blocks, 256, 0, h->stream>>>(h->F[0], h->F[1], h->bias, h->k, h->trip, h->trip + n, h->trip + 2 * n, n, h->partial); break;
     case 3: bpr_eval_loss_kernel<3><<<blocks, 256, 0, h->stream>>>(h->F[0], h->F[1], h->bias, h->k, h->trip, h->trip + n, h->trip + 2 * n, n, h->partial); break;
-    default: bpr_eval_loss_kernel<4><<<blocks, 256, 0, h->stream>>>(h->F[0], h->F[1], h->bias, h->k, h->trip, h->trip + n, h->trip + 2 * n, n, h->partial); break;
+    case 4: bpr_eval_loss_kernel<4><<<blocks, 256, 0, h->stream>>>(h->F[0], h->F[1], h->bias, h->k, h->trip, h->trip + n, h->trip + 2 * n, n, h->partial); break;
+    case 5: bpr_eval_loss_kernel<5><<<blocks, 256, 0, h->stream>>>(h->F[0], h->F[1], h->bias, h->k, h->trip, h->trip + n, h->trip + 2 * n, n, h->partial); break;
+    case 6: bpr_eval_loss_kernel<6><<<blocks, 256, 0, h->stream>>>(h->F[0], h->F[1], h->bias, h->k, h->trip, h->trip + n, h->trip + 2 * n, n, h->partial); break;
+    case 7: bpr_eval_loss_kernel<7><<<blocks, 256, 0, h->stream>>>(h->F[0], h->F[1], h->bias, h->k, h->trip, h->trip + n, h->trip + 2 * n, n, h->partial); break;
+    default: bpr_eval_loss_kernel<8><<<blocks, 256, 0, h->stream>>>(h->F[0], h->F[1], h->bias, h->k, h->trip, h->trip + n, h->trip + 2 * n, n, h->partial); break;
   }
   QMFB_CUDA(cudaGetLastError());
   sum_partials_kernel<<<1, 32, 0, h->stream>>>(h->partial, blocks, h->sum);

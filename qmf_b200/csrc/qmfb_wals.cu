@@ -1,6 +1,7 @@
 // C-ABI (include/qmf_b200.h) for the WALS half-step: launchers + the host-buffer engine handle.
 #include "qmfb_common.h"
 #include "wals_kernels.cuh"
+#include "wals_big.cuh"
 
 #include <algorithm>
 #include <numeric>
@@ -54,6 +55,50 @@ static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_su
   return QMFB_OK;
 }
 
+// ---- 128 < k <= 256: tiles in an L2-resident global workspace (wals_big.cuh) ----------------
+template <int NT>
+static int launch_gram_big(cudaStream_t st, const double* Y, int64_t ldy, int64_t r0, int64_t r1, double* ws, double* packed) {
+  using SM = WalsSmemBig<NT>;
+  static bool configured = false;
+  if (!configured) {
+    QMFB_CUDA(cudaFuncSetAttribute(gram_partial_big_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+    configured = true;
+  }
+  const int64_t n = r1 - r0;
+  const int parts = int(std::min<int64_t>(kGramMaxParts / 2, std::max<int64_t>(1, (n + 4 * kBigRows - 1) / (4 * kBigRows))));
+  gram_partial_big_kernel<NT><<<parts, SM::NTHREADS, SM::kBytes, st>>>(Y, ldy, r0, r1, ws);
+  QMFB_CUDA(cudaGetLastError());
+  const int nelem = SM::NTILE_A * 64;
+  gram_reduce_kernel<<<(nelem + 255) / 256, 256, 0, st>>>(ws, parts, nelem, packed);
+  QMFB_CUDA(cudaGetLastError());
+  return QMFB_OK;
+}
+
+template <int NT>
+static int launch_solve_big(cudaStream_t st, const SolveParams& prm, double* loss_sum, int32_t* scratch) {
+  using SM = WalsSmemBig<NT>;
+  static int sms = 0;
+  if (sms == 0) {
+    QMFB_CUDA(cudaFuncSetAttribute(wals_solve_big_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+    int dev = 0;
+    QMFB_CUDA(cudaGetDevice(&dev));
+    QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  QMFB_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(int32_t), st));
+  if (prm.nrows > 0) {
+    const int grid = int(std::min<int64_t>(sms, prm.nrows));
+    double* ws = nullptr;  // stream-ordered: concurrent solves on other streams get their own slice
+    QMFB_CUDA(cudaMallocAsync(&ws, size_t(grid) * SM::NTILE * 64 * sizeof(double), st));
+    wals_solve_big_kernel<NT><<<grid, SM::NTHREADS, SM::kBytes, st>>>(prm, ws);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(ws, st);
+    QMFB_CUDA(e);
+  }
+  sum_kernel<<<1, 1024, 0, st>>>(prm.row_loss, prm.nrows, loss_sum);
+  QMFB_CUDA(cudaGetLastError());
+  return QMFB_OK;
+}
+
 }  // namespace qmfb
 
 using namespace qmfb;
@@ -78,7 +123,7 @@ int qmfb_debug_set_flags(int flags) {
 #endif
 
 int qmfb_padded_k(int k) {
-  if (k < 1 || k > 128) return set_error(QMFB_ERR_UNSUPPORTED, "nfactors must be in [1, 128] (got %d)", k);
+  if (k < 1 || k > 256) return set_error(QMFB_ERR_UNSUPPORTED, "nfactors must be in [1, 256] (got %d)", k);
   return ((k + 31) / 32) * 32;
 }
 
@@ -105,6 +150,10 @@ int qmfb_gram_dev(void* stream, const double* Y, int64_t ldy, int64_t row_begin,
     case 8: return launch_gram<8>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
     case 12: return launch_gram<12>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
     case 16: return launch_gram<16>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
+    case 20: return launch_gram_big<20>(st, Y, ldy, row_begin, row_end, workspace, gram_packed);
+    case 24: return launch_gram_big<24>(st, Y, ldy, row_begin, row_end, workspace, gram_packed);
+    case 28: return launch_gram_big<28>(st, Y, ldy, row_begin, row_end, workspace, gram_packed);
+    case 32: return launch_gram_big<32>(st, Y, ldy, row_begin, row_end, workspace, gram_packed);
   }
   return set_error(QMFB_ERR_UNSUPPORTED, "unsupported padded k %d", kp);
 }
@@ -119,6 +168,10 @@ int qmfb_gram_unpack_dev(void* stream, const double* gram_packed, int k, double*
     case 8: gram_unpack_kernel<8><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
     case 12: gram_unpack_kernel<12><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
     case 16: gram_unpack_kernel<16><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
+    case 20: gram_unpack_kernel<20><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
+    case 24: gram_unpack_kernel<24><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
+    case 28: gram_unpack_kernel<28><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
+    case 32: gram_unpack_kernel<32><<<nb, 256, 0, st>>>(gram_packed, k, out); break;
   }
   QMFB_CUDA(cudaGetLastError());
   return QMFB_OK;
@@ -142,6 +195,10 @@ int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset
     case 8: return launch_solve<8>(st, prm, loss_sum, scratch);
     case 12: return launch_solve<12>(st, prm, loss_sum, scratch);
     case 16: return launch_solve<16>(st, prm, loss_sum, scratch);
+    case 20: return launch_solve_big<20>(st, prm, loss_sum, scratch);
+    case 24: return launch_solve_big<24>(st, prm, loss_sum, scratch);
+    case 28: return launch_solve_big<28>(st, prm, loss_sum, scratch);
+    case 32: return launch_solve_big<32>(st, prm, loss_sum, scratch);
   }
   return set_error(QMFB_ERR_UNSUPPORTED, "unsupported padded k %d", kp);
 }

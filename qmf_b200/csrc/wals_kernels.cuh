@@ -111,6 +111,7 @@ __device__ __forceinline__ void tile_mma_tn(double (&c)[2], const double* ta, co
 // ------------------------------------------------------------------------------------------
 template <int NT>
 struct WalsSmem {
+  static constexpr int kNT = NT;
   static constexpr int KP = NT * 8;            // padded factor dimension
   // staging row stride (doubles).  A 64-bit shared load is served per half-warp (16 lanes x 8 B =
   // one 128-byte wavefront); the DMMA fragment address is (lane%4)*LD + lane/4, so LD % 16 == 4
@@ -531,10 +532,13 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
 // 34+ accumulator registers otherwise push the operand fragments of the trailing update into local
 // memory (3 STL.64 + 3 LDL.64 per four tiles in profiles/r01_solve_final_ncu.csv).
 // Returns false on a non-positive pivot.
-template <int NT>
-__device__ __noinline__ bool solve_row(unsigned char* smem) {
-  using SM = WalsSmem<NT>;
-  double* tiles = reinterpret_cast<double*>(smem + SM::kOffTiles);
+// SM is the shared-memory layout (WalsSmem<NT>: tiles in shared memory; WalsSmemBig<NT>, k > 128:
+// GT = true and the tiles live in the CTA's L2-resident global workspace `gtiles`).
+template <class SM, bool GT>
+__device__ __noinline__ bool solve_row(unsigned char* smem, double* gtiles) {
+  constexpr int NT = SM::kNT;
+  constexpr int TU = GT ? 4 : kTU;  // L2-latency tiles: keep several in flight
+  double* tiles = GT ? gtiles : reinterpret_cast<double*>(smem + SM::kOffTiles);
   double* wt = reinterpret_cast<double*>(smem + SM::kOffW);
   double* bcopy = reinterpret_cast<double*>(smem + SM::kOffB);
   double* xvec = reinterpret_cast<double*>(smem + SM::kOffX);
@@ -608,11 +612,11 @@ __device__ __noinline__ bool solve_row(unsigned char* smem) {
     if (SM::NWARPS == 1 || warp != dwarp) {
       // flat enumeration of the trailing tiles (contiguous in storage); (J1, J2) decoded incrementally
       int J1 = I + 1, off = 1 + wslot;  // position `off` inside row J1 (row J1 has NT - J1 + 1 tiles)
-      for (int e = tstart + 1 + wslot; e < SM::NTILE; e += kTU * nw) {
+      for (int e = tstart + 1 + wslot; e < SM::NTILE; e += TU * nw) {
         // straight-line body: out-of-range slots of the last sweep recompute a valid tile and skip the store
-        double c[kTU][2], ua[kTU][2], ub[kTU][2];
+        double c[TU][2], ua[TU][2], ub[TU][2];
 #pragma unroll
-        for (int q = 0; q < kTU; ++q) {
+        for (int q = 0; q < TU; ++q) {
           const int ti = e + q * nw;
           const bool v = ti < SM::NTILE;
           if (v) {
@@ -630,12 +634,12 @@ __device__ __noinline__ bool solve_row(unsigned char* smem) {
           off += nw;
         }
 #pragma unroll
-        for (int q = 0; q < kTU; ++q) {
+        for (int q = 0; q < TU; ++q) {
           dmma(c[q], ua[q][0], ub[q][0]);
           dmma(c[q], ua[q][1], ub[q][1]);
         }
 #pragma unroll
-        for (int q = 0; q < kTU; ++q) {
+        for (int q = 0; q < TU; ++q) {
           const int ti = e + q * nw;
           if (ti < SM::NTILE) *reinterpret_cast<double2*>(tiles + size_t(ti) * 64 + co) = make_double2(c[q][0], c[q][1]);
         }
@@ -756,7 +760,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       np1 = __ldg(prm.row_ptr + nrow + 1);
     }
     __syncthreads();
-    if (!solve_row<NT>(smem) && lane == 0) *prm.error = 1;
+    if (!solve_row<SM, false>(smem, nullptr) && lane == 0) *prm.error = 1;
     __syncthreads();
     QMFB_T(tp5);
     // ---- loss term: c + x^T B x - 2 x^T b with x^T B x = z^T z - lambda x^T x (WALSEngine.cpp:295-304)

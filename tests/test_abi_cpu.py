@@ -31,7 +31,10 @@ def test_layout_helpers():
     from qmf_b200 import capi
     lib = capi.lib
     assert [lib.qmfb_padded_k(k) for k in (1, 30, 32, 33, 64, 100, 128)] == [32, 32, 32, 64, 64, 128, 128]
-    assert lib.qmfb_padded_k(129) < 0 and "nfactors" in capi.last_error()
+    assert [lib.qmfb_padded_k(k) for k in (129, 160, 200, 256)] == [160, 160, 224, 256]
+    assert lib.qmfb_padded_k(0) < 0
+    assert lib.qmfb_padded_k(257) < 0 and "nfactors" in capi.last_error()
+    assert lib.qmfb_gram_packed_len(256) == 528 * 64
     assert lib.qmfb_gram_packed_len(128) == 136 * 64
     assert lib.qmfb_gram_packed_len(30) == 10 * 64
     assert lib.qmfb_gram_workspace_len(64) == 36 * 64 * 296

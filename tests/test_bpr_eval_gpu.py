@@ -20,7 +20,8 @@ def _planted(nu, ni, npairs, seed, rank=6):
     return u, i, S
 
 
-@pytest.mark.parametrize("k,biases", [(30, True), (30, False), (64, True), (100, False), (7, True), (128, True)])
+@pytest.mark.parametrize("k,biases", [(30, True), (30, False), (64, True), (100, False), (7, True), (128, True),
+                                      (160, False), (256, True)])
 def test_update_triplets_match_oracle(oracle_lib, k, biases):
     from qmf_b200.bpr import BprEngineHandle
     import oracle
@@ -184,10 +185,10 @@ def test_unsupported_shapes_fail_loudly():
     from qmf_b200.bpr import BprEngineHandle
     from qmf_b200.wals import WalsEngineHandle
     with pytest.raises(capi.QmfbError) as e:
-        WalsEngineHandle(10, 10, 129)
+        WalsEngineHandle(10, 10, 257)
     assert e.value.code == -5 and "nfactors" in str(e.value)
     with pytest.raises(capi.QmfbError):
-        BprEngineHandle(10, 10, 200)
+        BprEngineHandle(10, 10, 300)
     h = BprEngineHandle(3, 3, 4)
     with pytest.raises(capi.QmfbError):
         h.get_biases()              # "can't access bias when withBiases = false" (qmf/FactorData.h:45-48)
