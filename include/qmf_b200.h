@@ -164,6 +164,27 @@ int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double*
                        const double* biases, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
                        const int32_t* label_items, int64_t nlabels, int32_t* cnt, double* pos_scores, int32_t* error);
 
+/* ---- dataset ingest on the GPU ------------------------------------------
+ * Replaces IdIndex (qmf/utils/IdIndex.h) + WALSEngine::groupSignals / sortDataset
+ * (qmf/wals/WALSEngine.cpp:130-163): raw (user id, item id, value) cells in file order ->
+ * dense indices (idx = rank of the id among the distinct ids, the reference's assignment) and both
+ * CSR orientations (rows by row id, cells by column id, duplicates kept in file order) plus the
+ * longest-first row order the solve kernel deals rows in.  Inputs are host arrays. */
+typedef struct qmfb_signals qmfb_signals_t;
+int qmfb_signals_build(int device, int64_t nnz, const int64_t* user_ids, const int64_t* item_ids, const double* values,
+                       qmfb_signals_t** out);
+int qmfb_signals_destroy(qmfb_signals_t* s);
+int qmfb_signals_dims(const qmfb_signals_t* s, int64_t* nusers, int64_t* nitems, int64_t* nnz);
+/* ids_host[idx] = raw id of dense index idx (n[side] entries, ascending) */
+int qmfb_signals_ids(const qmfb_signals_t* s, int side, int64_t* ids_host);
+/* host copies of one orientation (side = QMFB_SIDE_USER: rows are users); any pointer may be NULL */
+int qmfb_signals_csr(const qmfb_signals_t* s, int side, int64_t* row_ptr, int32_t* col_idx, double* val, int32_t* order);
+/* device pointers of one orientation (owned by the handle) */
+int qmfb_signals_device(const qmfb_signals_t* s, int side, const int64_t** row_ptr, const int32_t** col_idx, const double** val,
+                        const int32_t** order);
+/* give a WALS engine (created with the handle's nusers / nitems) both orientations, device to device */
+int qmfb_wals_set_signals(qmfb_wals_t* h, const qmfb_signals_t* s);
+
 #ifdef __cplusplus
 }
 #endif

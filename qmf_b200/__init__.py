@@ -10,6 +10,7 @@ no CPU fallback.  ``qmf_b200.datagen`` (synthetic dataset shapes) has no such de
 _LAZY = {
     "WalsEngineHandle": ("qmf_b200.wals", "WalsEngineHandle"),
     "csr_from_coo": ("qmf_b200.wals", "csr_from_coo"),
+    "Signals": ("qmf_b200.wals", "Signals"),
     "ShardedWals": ("qmf_b200.wals_dist", "ShardedWals"),
     "BprEngineHandle": ("qmf_b200.bpr", "BprEngineHandle"),
 }

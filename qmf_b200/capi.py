@@ -78,6 +78,13 @@ _SIG = {
                                  p_f64]),
     "qmfb_eval_rank_dev": (C.c_int, [vp, vp, c_i64, vp, c_i64, c_i64, C.c_int, vp, vp, c_i64, vp, vp, c_i64, vp, vp,
                                      vp]),
+    "qmfb_signals_build": (C.c_int, [C.c_int, c_i64, p_i64, p_i64, p_f64, C.POINTER(vp)]),
+    "qmfb_signals_destroy": (C.c_int, [vp]),
+    "qmfb_signals_dims": (C.c_int, [vp, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
+    "qmfb_signals_ids": (C.c_int, [vp, C.c_int, p_i64]),
+    "qmfb_signals_csr": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
+    "qmfb_signals_device": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "qmfb_wals_set_signals": (C.c_int, [vp, vp]),
 }
 
 EXPORTS = tuple(_SIG)

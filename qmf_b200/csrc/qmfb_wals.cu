@@ -332,6 +332,42 @@ int qmfb_wals_set_csr(qmfb_wals_t* h, int side, int64_t row_begin, int64_t nrows
   return QMFB_OK;
 }
 
+int qmfb_wals_set_signals(qmfb_wals_t* h, const qmfb_signals_t* s) {
+  int64_t nu = 0, ni = 0, nnz = 0;
+  if (!h || !s || qmfb_signals_dims(s, &nu, &ni, &nnz) != QMFB_OK) return set_error(QMFB_ERR_INVALID, "qmfb_wals_set_signals: bad argument");
+  if (nu != h->n[0] || ni != h->n[1]) {
+    return set_error(QMFB_ERR_INVALID, "qmfb_wals_set_signals: engine is %lld x %lld, signals are %lld x %lld", (long long)h->n[0],
+                     (long long)h->n[1], (long long)nu, (long long)ni);
+  }
+  QMFB_CUDA(cudaSetDevice(h->device));
+  for (int side = 0; side < 2; ++side) {
+    const int64_t* rp = nullptr;
+    const int32_t* col = nullptr;
+    const double* val = nullptr;
+    const int32_t* order = nullptr;
+    if (int rc = qmfb_signals_device(s, side, &rp, &col, &val, &order)) return rc;
+    const int64_t nrows = h->n[side];
+    cudaFree(h->row_ptr[side]);
+    cudaFree(h->col[side]);
+    cudaFree(h->val[side]);
+    cudaFree(h->order[side]);
+    h->row_ptr[side] = nullptr; h->col[side] = nullptr; h->val[side] = nullptr; h->order[side] = nullptr;
+    QMFB_CUDA(cudaMalloc(&h->row_ptr[side], size_t(nrows + 1) * sizeof(int64_t)));
+    QMFB_CUDA(cudaMalloc(&h->col[side], size_t(nnz) * sizeof(int32_t)));
+    QMFB_CUDA(cudaMalloc(&h->val[side], size_t(nnz) * sizeof(double)));
+    QMFB_CUDA(cudaMalloc(&h->order[side], size_t(nrows) * sizeof(int32_t)));
+    QMFB_CUDA(cudaMemcpyAsync(h->row_ptr[side], rp, size_t(nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
+    QMFB_CUDA(cudaMemcpyAsync(h->col[side], col, size_t(nnz) * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    QMFB_CUDA(cudaMemcpyAsync(h->val[side], val, size_t(nnz) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    QMFB_CUDA(cudaMemcpyAsync(h->order[side], order, size_t(nrows) * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    h->row_begin[side] = 0;
+    h->nrows[side] = nrows;
+    h->nnz[side] = nnz;
+  }
+  QMFB_CUDA(cudaStreamSynchronize(h->stream));
+  return QMFB_OK;
+}
+
 int qmfb_wals_set_factors(qmfb_wals_t* h, int side, const double* host) {
   if (!h || side < 0 || side > 1 || !host) return set_error(QMFB_ERR_INVALID, "qmfb_wals_set_factors: bad argument");
   QMFB_CUDA(cudaSetDevice(h->device));

@@ -5,6 +5,10 @@
 #include <memory>
 #include <sstream>
 
+#include <cstring>
+#include <fstream>
+#include <random>
+#include <algorithm>
 #include <qmf/DatasetReader.h>
 #include <qmf/Engine.h>
 #include <qmf/Matrix.h>
@@ -113,6 +117,54 @@ int main() {
     EXPECT(d.size() == 2 && d[0].userId == 1 && d[0].itemId == 2 && d[0].value == 3.0 && d[1].userId == -4 && d[1].value == 0.5);
     const auto parts = qmf::split("auc,,p@10,", ',');
     EXPECT(parts.size() == 2 && parts[0] == "auc" && parts[1] == "p@10");
+  }
+  // the mapped multi-threaded readAll() returns exactly what the getline + sscanf loop returns
+  {
+    const std::string path = "/tmp/qmf_b200_selftest_dataset.txt";
+    std::mt19937_64 gen(7);
+    const char* weights[] = {"1", "0.5", "3.25", "1e-3", "2.5E+2", "-0", "007.1250", ".5", "5.", "0.1", "0.30000000000000004",
+                             "123456789012345678", "1.7976931348623157e308", "4.9e-324", "inf", "nan", "0x1.8p1", "1e",
+                             "17.000000000000000000001", "0.000000000000000000000012345", "9007199254740993", "3.14abc"};
+    {
+      std::ofstream out(path);
+      for (int n = 0; n < 300000; ++n) {
+        const long long u = (long long)(gen() % 2000003) - 1000, i = (long long)(gen() % 50021);
+        const char* sep1 = (n % 7 == 0) ? "\t" : " ";
+        const char* sep2 = (n % 11 == 0) ? "   " : " ";
+        if (n % 13 == 0) out << "  ";
+        if (n % 17 == 0 && u >= 0) out << '+';
+        out << u << sep1 << i << sep2 << weights[gen() % (sizeof(weights) / sizeof(weights[0]))];
+        if (n % 19 == 0) out << " trailing";
+        if (n % 23 == 0) out << '\r';
+        out << '\n';
+      }
+      out << "9223372036854775808 -9223372036854775809 1\n";  // clamped like strtoll
+      out << "5 6 7";                                           // last line without a newline
+    }
+    std::vector<qmf::DatasetElem> slow, fast;
+    {
+      qmf::DatasetReader reader(path);
+      qmf::DatasetElem e;
+      while (reader.readOne(e)) slow.push_back(e);
+    }
+    {
+      qmf::DatasetReader reader(path);
+      reader.readAll(fast);
+    }
+    EXPECT(slow.size() == 300002 && fast.size() == slow.size());
+    size_t diff = 0;
+    for (size_t n = 0; n < std::min(slow.size(), fast.size()); ++n) {
+      diff += slow[n].userId != fast[n].userId || slow[n].itemId != fast[n].itemId ||
+              std::memcmp(&slow[n].value, &fast[n].value, sizeof(double)) != 0;
+    }
+    EXPECT(diff == 0);
+    EXPECT(fast[300000].userId == INT64_MAX && fast[300000].itemId == INT64_MIN);
+    qmf::DatasetElem e;
+    EXPECT(!qmf::DatasetReader::parseLine("1 2", "1 2" + 3, e));
+    EXPECT(!qmf::DatasetReader::parseLine("", "", e));
+    EXPECT(!qmf::DatasetReader::parseLine("1 x 3", "1 x 3" + 5, e));
+    EXPECT(!qmf::DatasetReader::parseLine("1 2 .", "1 2 ." + 5, e));
+    std::remove(path.c_str());
   }
   // averaging order of Metric::compute(labels, scores, parallel)
   EXPECT(qmf::averageOverUsers({1.0, 2.0, 3.0, 4.0, 5.0}, 2) == ((1.0 + 3.0 + 5.0) + (2.0 + 4.0)) / 5);

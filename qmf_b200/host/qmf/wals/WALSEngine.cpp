@@ -15,36 +15,6 @@ namespace {
     CHECK_EQ(qmfb_rc_, 0) << #call << ": " << qmfb_last_error();    \
   } while (0)
 
-struct Cell {
-  int64_t row, col;
-  Double value;
-};
-
-// sort by (row id, col id) and cut into rows; the dense index of a row is its rank
-void buildCsr(std::vector<Cell>& cells, IdIndex& rowIndex, WALSEngine::Csr& csr) {
-  std::sort(cells.begin(), cells.end(), [](const Cell& a, const Cell& b) {
-    return a.row != b.row ? a.row < b.row : a.col < b.col;
-  });
-  csr.rowPtr.assign(1, 0);
-  for (size_t p = 0; p < cells.size(); ++p) {
-    if (p == 0 || cells[p].row != cells[p - 1].row) {
-      if (p != 0) csr.rowPtr.push_back(int64_t(p));
-      const size_t idx = rowIndex.getOrSetIdx(cells[p].row);
-      CHECK_EQ(idx + 1, csr.rowPtr.size());
-    }
-  }
-  if (!cells.empty()) csr.rowPtr.push_back(int64_t(cells.size()));
-}
-
-void fillCols(const std::vector<Cell>& cells, const IdIndex& colIndex, WALSEngine::Csr& csr) {
-  csr.col.resize(cells.size());
-  csr.val.resize(cells.size());
-  for (size_t p = 0; p < cells.size(); ++p) {
-    csr.col[p] = int32_t(colIndex.idx(cells[p].col));
-    csr.val[p] = cells[p].value;
-  }
-}
-
 }  // namespace
 
 WALSEngine::WALSEngine(const WALSConfig& config, const std::unique_ptr<MetricsEngine>& metricsEngine, const size_t nthreads)
@@ -62,15 +32,30 @@ WALSEngine::~WALSEngine() {
 void WALSEngine::init(const std::vector<DatasetElem>& dataset) {
   CHECK(!userFactors_ && !itemFactors_) << "engine was already initialized with train data";
   CHECK(!dataset.empty()) << "empty training dataset";
-  std::vector<Cell> byUser(dataset.size()), byItem(dataset.size());
-  for (size_t p = 0; p < dataset.size(); ++p) {
-    byUser[p] = Cell{dataset[p].userId, dataset[p].itemId, dataset[p].value};
-    byItem[p] = Cell{dataset[p].itemId, dataset[p].userId, dataset[p].value};
+  // Dense indices + both CSR orientations are built on the GPU (qmfb_signals_*): idx = rank of the
+  // raw id among the distinct ids, rows by row id, cells by column id - what IdIndex +
+  // groupSignals / sortDataset produce (qmf/wals/WALSEngine.cpp:130-163), without the two host
+  // sorts of the whole dataset.
+  qmfb_signals_t* signals = nullptr;
+  {
+    std::vector<int64_t> uid(dataset.size()), iid(dataset.size());
+    std::vector<double> val(dataset.size());
+    for (size_t p = 0; p < dataset.size(); ++p) {
+      uid[p] = dataset[p].userId;
+      iid[p] = dataset[p].itemId;
+      val[p] = dataset[p].value;
+    }
+    QMFB_OK_OR_DIE(qmfb_signals_build(config_.device, int64_t(dataset.size()), uid.data(), iid.data(), val.data(), &signals));
   }
-  buildCsr(byUser, userIndex_, csr_[0]);
-  buildCsr(byItem, itemIndex_, csr_[1]);
-  fillCols(byUser, itemIndex_, csr_[0]);
-  fillCols(byItem, userIndex_, csr_[1]);
+  int64_t nu = 0, ni = 0;
+  QMFB_OK_OR_DIE(qmfb_signals_dims(signals, &nu, &ni, nullptr));
+  {
+    std::vector<int64_t> ids(static_cast<size_t>(std::max(nu, ni)));
+    QMFB_OK_OR_DIE(qmfb_signals_ids(signals, QMFB_SIDE_USER, ids.data()));
+    for (int64_t r = 0; r < nu; ++r) CHECK_EQ(userIndex_.getOrSetIdx(ids[size_t(r)]), size_t(r));
+    QMFB_OK_OR_DIE(qmfb_signals_ids(signals, QMFB_SIDE_ITEM, ids.data()));
+    for (int64_t r = 0; r < ni; ++r) CHECK_EQ(itemIndex_.getOrSetIdx(ids[size_t(r)]), size_t(r));
+  }
 
   userFactors_ = std::make_unique<FactorData>(nusers(), config_.nfactors);
   itemFactors_ = std::make_unique<FactorData>(nitems(), config_.nfactors);
@@ -84,10 +69,8 @@ void WALSEngine::init(const std::vector<DatasetElem>& dataset) {
   }
 
   QMFB_OK_OR_DIE(qmfb_wals_create(config_.device, int64_t(nusers()), int64_t(nitems()), int(config_.nfactors), &dev_));
-  QMFB_OK_OR_DIE(qmfb_wals_set_csr(dev_, QMFB_SIDE_USER, 0, int64_t(nusers()), csr_[0].rowPtr.data(), csr_[0].col.data(),
-                                   csr_[0].val.data()));
-  QMFB_OK_OR_DIE(qmfb_wals_set_csr(dev_, QMFB_SIDE_ITEM, 0, int64_t(nitems()), csr_[1].rowPtr.data(), csr_[1].col.data(),
-                                   csr_[1].val.data()));
+  QMFB_OK_OR_DIE(qmfb_wals_set_signals(dev_, signals));
+  qmfb_signals_destroy(signals);
   QMFB_OK_OR_DIE(qmfb_wals_set_factors(dev_, QMFB_SIDE_ITEM, itemFactors_->getFactors().data()));
 }
 

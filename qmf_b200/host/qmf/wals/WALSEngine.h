@@ -38,16 +38,6 @@ class WALSEngine : public Engine {
   size_t nusers() const { return userIndex_.size(); }
   size_t nitems() const { return itemIndex_.size(); }
 
-  // CSR of one orientation exactly as WALSEngine::groupSignals builds its signal groups
-  // (qmf/wals/WALSEngine.cpp:130-163): rows in ascending raw id, entries in ascending raw id of
-  // the other side, duplicates kept; col holds the dense idx (== rank) of the other side.
-  struct Csr {
-    std::vector<int64_t> rowPtr;
-    std::vector<int32_t> col;
-    std::vector<Double> val;
-  };
-  const Csr& userCsr() const { return csr_[0]; }
-  const Csr& itemCsr() const { return csr_[1]; }
   const FactorData& userFactors() const { return *userFactors_; }
   const FactorData& itemFactors() const { return *itemFactors_; }
 
@@ -61,7 +51,6 @@ class WALSEngine : public Engine {
   const size_t nthreads_;
 
   IdIndex userIndex_, itemIndex_;
-  Csr csr_[2];
   std::unique_ptr<FactorData> userFactors_, itemFactors_;  // host mirrors
   mutable bool hostStale_ = false;
   qmfb_wals* dev_ = nullptr;

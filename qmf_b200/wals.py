@@ -30,6 +30,45 @@ def csr_from_coo(row_id, col_id, val, col_ids_sorted=None):
     return ids, row_ptr, col_idx, np.ascontiguousarray(v)
 
 
+class Signals:
+    """GPU-built dense indexing + both CSR orientations of a raw (user id, item id, value) dataset
+    (qmfb_signals_*: IdIndex + WALSEngine::groupSignals on the device)."""
+
+    def __init__(self, user_ids, item_ids, values, device=0):
+        u = np.ascontiguousarray(user_ids, dtype=np.int64)
+        i = np.ascontiguousarray(item_ids, dtype=np.int64)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert u.shape == i.shape == v.shape and u.ndim == 1
+        self._h = None
+        h = C.c_void_p()
+        check(lib.qmfb_signals_build(device, u.size, u, i, v, C.byref(h)))
+        self._h = h
+        nu, ni, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.qmfb_signals_dims(h, C.byref(nu), C.byref(ni), C.byref(nnz)))
+        self.nusers, self.nitems, self.nnz = nu.value, ni.value, nnz.value
+
+    def close(self):
+        if self._h:
+            lib.qmfb_signals_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def ids(self, side):
+        out = np.empty(self.nusers if side == SIDE_USER else self.nitems, dtype=np.int64)
+        check(lib.qmfb_signals_ids(self._h, side, out))
+        return out
+
+    def csr(self, side):
+        """(row_ptr, col_idx, val, order) host copies of one orientation."""
+        n = self.nusers if side == SIDE_USER else self.nitems
+        rp, col = np.empty(n + 1, np.int64), np.empty(self.nnz, np.int32)
+        val, order = np.empty(self.nnz, np.float64), np.empty(n, np.int32)
+        check(lib.qmfb_signals_csr(self._h, side, rp.ctypes.data, col.ctypes.data, val.ctypes.data, order.ctypes.data))
+        return rp, col, val, order
+
+
 class WalsEngineHandle:
     """Engine-level handle: host buffers in, host buffers out (single GPU)."""
 
@@ -50,6 +89,9 @@ class WalsEngineHandle:
 
     def _n(self, side):
         return self.nusers if side == SIDE_USER else self.nitems
+
+    def set_signals(self, signals):
+        check(lib.qmfb_wals_set_signals(self._h, signals._h))
 
     def set_csr(self, side, row_ptr, col_idx, val, row_begin=0):
         row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
