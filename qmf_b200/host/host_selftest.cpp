@@ -118,6 +118,34 @@ int main() {
     const auto parts = qmf::split("auc,,p@10,", ',');
     EXPECT(parts.size() == 2 && parts[0] == "auc" && parts[1] == "p@10");
   }
+  // the block-parallel saveFactors writes the bytes of the sequential "id [bias] f0 f1 ...\n" writer
+  {
+    const size_t n = 70001, k = 5;
+    qmf::FactorData f(n, k, true);
+    qmf::IdIndex index;
+    std::mt19937_64 gen(3);
+    std::uniform_real_distribution<double> dist(-3.0, 3.0);
+    f.setFactors([&](size_t, size_t) { return dist(gen); });
+    std::ostringstream want;
+    for (size_t r = 0; r < n; ++r) {
+      index.getOrSetIdx(int64_t(r) * 3 - 100);
+      f.biasAt(r) = dist(gen);
+    }
+    for (size_t r = 0; r < n; ++r) {
+      char num[64];
+      want << (int64_t(r) * 3 - 100);
+      std::snprintf(num, sizeof num, " %.9f", f.biasAt(r));
+      want << num;
+      for (size_t c = 0; c < k; ++c) {
+        std::snprintf(num, sizeof num, " %.9f", f.at(r, c));
+        want << num;
+      }
+      want << '\n';
+    }
+    std::ostringstream got;
+    qmf::Engine::saveFactors(f, index, got);
+    EXPECT(got.str() == want.str());
+  }
   // the mapped multi-threaded readAll() returns exactly what the getline + sscanf loop returns
   {
     const std::string path = "/tmp/qmf_b200_selftest_dataset.txt";
