@@ -321,7 +321,7 @@ def run_ours(args, cfg, workload):
     nu, ni, nnz, k = cfg
 
     csr_user, csr_item = uniform_csr_torch(nu, ni, nnz, seed=20240501, device=device)
-    sw = ShardedWals(nu, ni, k, csr_user, csr_item, device, rank, world)
+    sw = ShardedWals(nu, ni, k, csr_user, csr_item, device, rank, world, exchange=args.exchange)
     Y0 = init_item_factors(ni, k, seed=7)
     sw.set_factors(1, Y0)
     torch.cuda.synchronize()
@@ -477,12 +477,13 @@ def run_ours(args, cfg, workload):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "s_per_epoch": ms_per_step * 1e-3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "nusers": nu, "nitems": ni, "nnz": nnz, "nfactors": k, "alpha": ALPHA,
-                       "lambda": LAMBDA, "parallelism": "rows x%d" % world,
+                       "lambda": LAMBDA, "parallelism": "rows x%d" % world, "exchange": sw.exchange if world > 1 else "none",
                        "l2": "inputs (2.9 GB) larger than the 126 MB L2; no flush"},
             "loss": loss_value, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
             "cpu_baseline": cpu_baseline, "bpr": bpr, "eval": evalr, "lib": os.path.relpath(capi.LIB_PATH, ROOT),
         }
         print(json.dumps(line), flush=True)
+    sw.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -497,6 +498,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bpr", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: how the solved shards reach the other ranks (p2p = peer stores fused into the solve kernel)")
     args = ap.parse_args()
     from qmf_b200.datagen import CONFIGS
     cfg = CONFIGS[args.workload]

@@ -66,6 +66,21 @@ int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset
                         const int64_t* row_ptr, const int32_t* col, const double* val, const int32_t* order,
                         int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
                         double* loss_sum, int32_t* scratch);
+/* Same, with the all-gather of the solved shard FUSED into the kernel: every solved row is also
+ * stored into row (row_offset + local row) of the `npeers` replicas peer_X[0..npeers) (device
+ * pointers into the other ranks' factor matrices, same ldx; peer memory over NVLink, mapped with
+ * qmfb_ipc_open).  The caller orders the next reader after all ranks' kernels (any collective that
+ * follows the kernel on every rank's stream does, e.g. the allreduce of the loss). */
+int qmfb_wals_solve_peers_dev(void* stream, double* X, int64_t ldx, int64_t row_offset, const double* Y, int64_t ldy, int k,
+                              const int64_t* row_ptr, const int32_t* col_idx, const double* val, const int32_t* order,
+                              int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
+                              double* loss_sum, int32_t* scratch, double* const* peer_X, int npeers);
+/* Device buffers shareable between the ranks of one box (one process per GPU): allocate (zeroed) +
+ * export a 64-byte CUDA IPC handle; map another rank's buffer; unmap; free. */
+int qmfb_ipc_alloc(int device, int64_t bytes, void** ptr, void* handle64);
+int qmfb_ipc_open(int device, const void* handle64, void** ptr);
+int qmfb_ipc_close(void* ptr);
+int qmfb_ipc_free(void* ptr);
 
 /* ---------------------------------------------------------------- WALS engine (host) ------- */
 typedef struct qmfb_wals qmfb_wals_t;

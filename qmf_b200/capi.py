@@ -46,6 +46,12 @@ _SIG = {
     "qmfb_gram_unpack_dev": (C.c_int, [vp, vp, C.c_int, vp]),
     "qmfb_wals_solve_dev": (C.c_int, [vp, vp, c_i64, c_i64, vp, c_i64, C.c_int, vp, vp, vp, vp, c_i64, vp, c_f64, c_f64,
                                       vp, vp, vp]),
+    "qmfb_wals_solve_peers_dev": (C.c_int, [vp, vp, c_i64, c_i64, vp, c_i64, C.c_int, vp, vp, vp, vp, c_i64, vp, c_f64,
+                                            c_f64, vp, vp, vp, C.POINTER(vp), C.c_int]),
+    "qmfb_ipc_alloc": (C.c_int, [C.c_int, c_i64, C.POINTER(vp), C.c_char_p]),
+    "qmfb_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(vp)]),
+    "qmfb_ipc_close": (C.c_int, [vp]),
+    "qmfb_ipc_free": (C.c_int, [vp]),
     "qmfb_wals_create": (C.c_int, [C.c_int, c_i64, c_i64, C.c_int, C.POINTER(vp)]),
     "qmfb_wals_destroy": (C.c_int, [vp]),
     "qmfb_wals_set_csr": (C.c_int, [vp, C.c_int, c_i64, c_i64, p_i64, p_i32, p_f64]),

@@ -181,14 +181,26 @@ int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset
                         const int64_t* row_ptr, const int32_t* col, const double* val, const int32_t* order,
                         int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
                         double* loss_sum, int32_t* scratch) {
+  return qmfb_wals_solve_peers_dev(stream, X, ldx, row_offset, Y, ldy, k, row_ptr, col, val, order, nrows, gram_packed, alpha,
+                                   lambda, row_loss, loss_sum, scratch, nullptr, 0);
+}
+
+int qmfb_wals_solve_peers_dev(void* stream, double* X, int64_t ldx, int64_t row_offset, const double* Y, int64_t ldy, int k,
+                              const int64_t* row_ptr, const int32_t* col, const double* val, const int32_t* order,
+                              int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
+                              double* loss_sum, int32_t* scratch, double* const* peer_X, int npeers) {
   const int kp = qmfb_padded_k(k);
   if (kp < 0) return kp;
   if (ldx < kp || ldy < kp || nrows < 0 || nrows > INT32_MAX || !X || !Y || !row_ptr || !order || !gram_packed || !row_loss ||
-      !loss_sum || !scratch) {
+      !loss_sum || !scratch || npeers < 0 || npeers > kMaxPeers || (npeers > 0 && !peer_X)) {
     return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_dev: bad argument");
   }
   SolveParams prm{X, ldx, row_offset, Y, ldy, k, row_ptr, col, val, order, int(nrows), gram_packed, alpha, lambda,
-                  row_loss, scratch + 1};
+                  row_loss, scratch + 1, npeers, {}};
+  for (int p = 0; p < npeers; ++p) {
+    if (!peer_X[p]) return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_peers_dev: null peer pointer %d", p);
+    prm.peerX[p] = peer_X[p];
+  }
   auto st = static_cast<cudaStream_t>(stream);
   switch (kp / 8) {
     case 4: return launch_solve<4>(st, prm, loss_sum, scratch);

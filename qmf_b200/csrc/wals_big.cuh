@@ -189,9 +189,8 @@ __global__ void __launch_bounds__(WalsSmemBig<NT>::NTHREADS, 1) wals_solve_big_k
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
       if (lane == 0) prm.row_loss[row] = part;
-    } else if (warp == 1) {
-      double* xr = prm.X + (prm.row_offset + row) * prm.ldx;
-      for (int i = lane; i < SM::KP; i += 32) xr[i] = i < prm.k ? xvec[i] : 0.0;
+    } else {
+      store_solved_row(prm, xvec, prm.row_offset + row, SM::KP, warp - 1, lane, 0, SM::NWARPS - 1);
     }
   }
 }

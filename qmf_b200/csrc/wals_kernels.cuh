@@ -304,6 +304,8 @@ __global__ void gram_unpack_kernel(const double* __restrict__ packed, int k, dou
 // ------------------------------------------------------------------------------------------
 // fused per-row kernel
 // ------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 15;  // other ranks of one box
+
 struct SolveParams {
   double* X;              // left factors being solved (row stride ldx), global row = row_offset + local row
   int64_t ldx;
@@ -320,7 +322,23 @@ struct SolveParams {
   double alpha, lambda;
   double* row_loss;       // per local row loss term (WALSEngine.cpp:295-304)
   int* error;             // set to 1 if a pivot is not positive (reference: CHECK_EQ(result, 0), Matrix.cpp:94)
+  // Fused all-gather of the solved shard (multi-GPU): every solved row is ALSO stored into the same
+  // row of the other ranks' replicas of X, straight from the solve kernel over NVLink peer memory
+  // (same ldx / row_offset), instead of a separate collective after the kernel.
+  int npeers;
+  double* peerX[kMaxPeers];
 };
+
+// Store the solved row (KP doubles in shared memory) to X and to every peer replica.  Target t is
+// written by warp (first + t) mod nwarps; posted stores, nothing waits for NVLink.
+__device__ __forceinline__ void store_solved_row(const SolveParams& prm, const double* xvec, int64_t grow, int KP, int warp,
+                                                 int lane, int first, int nwarps) {
+  for (int t = 0; t <= prm.npeers; ++t) {
+    if ((first + t) % nwarps != warp) continue;
+    double* xr = (t == 0 ? prm.X : prm.peerX[t - 1]) + grow * prm.ldx;
+    for (int i = lane; i < KP; i += 32) xr[i] = i < prm.k ? xvec[i] : 0.0;
+  }
+}
 
 
 
@@ -775,9 +793,11 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
       if (lane == 0) prm.row_loss[cs->row] = part;
-    } else if (warp == 1 || SM::NWARPS == 1) {
-      double* xr = prm.X + (prm.row_offset + cs->row) * prm.ldx;
-      for (int i = lane; i < SM::KP; i += 32) xr[i] = i < prm.k ? xvec[i] : 0.0;
+    }
+    if (SM::NWARPS == 1) {
+      store_solved_row(prm, xvec, prm.row_offset + cs->row, SM::KP, 0, lane, 0, 1);
+    } else if (warp != 0) {
+      store_solved_row(prm, xvec, prm.row_offset + cs->row, SM::KP, warp - 1, lane, 0, SM::NWARPS - 1);
     }
     // ---- next row -----------------------------------------------------------------------------------
     if (tid == 0) {

@@ -7,8 +7,11 @@ its user range and the CSC rows of its item range.  One half-step "update side S
   1. partial Gram over THIS rank's rows of the other side   (qmfb_gram_dev)
   2. allreduce(sum) of the packed Gram (<= 68 KB)            (NCCL)
   3. solve this rank's rows of S                             (qmfb_wals_solve_dev)
-  4. broadcast each rank's freshly solved rows to all        (NCCL, unequal shards allowed)
-  5. allreduce(sum) of the loss scalar                       (NCCL)
+  4. every solved row also goes into the other ranks' replicas, FROM the solve kernel, as
+     peer-memory stores over NVLink (qmfb_wals_solve_peers_dev; replicas are CUDA-IPC buffers) -
+     there is no separate all-gather.  (exchange="nccl": one broadcast per rank instead.)
+  5. allreduce(sum) of the loss scalar                       (NCCL) - which also orders the next
+     half-step's reads after every rank's peer stores
 
 torch is used for device memory, streams and torch.distributed only.  With world == 1 no
 collective is issued.  The same class runs on CPU tensors with the `gloo` backend when a
@@ -67,27 +70,64 @@ class CudaKernels:
         self.capi.check(self.lib.qmfb_gram_dev(self._stream(), Y.data_ptr(), Y.stride(0), row_begin, row_end, k,
                                                ws.data_ptr(), out.data_ptr()))
 
-    def solve(self, X, row_offset, Y, k, row_ptr, col, val, order, gram, alpha, lam, row_loss, loss_sum, scratch):
-        self.capi.check(self.lib.qmfb_wals_solve_dev(
+    def solve(self, X, row_offset, Y, k, row_ptr, col, val, order, gram, alpha, lam, row_loss, loss_sum, scratch,
+              peers=()):
+        """peers: raw device pointers of the other ranks' replicas of X (fused all-gather)"""
+        arr = (C.c_void_p * max(len(peers), 1))(*peers)
+        self.capi.check(self.lib.qmfb_wals_solve_peers_dev(
             self._stream(), X.data_ptr(), X.stride(0), row_offset, Y.data_ptr(), Y.stride(0), k, row_ptr.data_ptr(),
             col.data_ptr(), val.data_ptr(), order.data_ptr(), order.numel(), gram.data_ptr(), alpha, lam,
-            row_loss.data_ptr(), loss_sum.data_ptr(), scratch.data_ptr()))
+            row_loss.data_ptr(), loss_sum.data_ptr(), scratch.data_ptr(), arr, len(peers)))
+
+    # ---- replicas shareable between the ranks of one box (CUDA IPC) ----
+    def ipc_alloc(self, device_index, nbytes):
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        self.capi.check(self.lib.qmfb_ipc_alloc(device_index, nbytes, C.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def ipc_open(self, device_index, handle):
+        ptr = C.c_void_p()
+        self.capi.check(self.lib.qmfb_ipc_open(device_index, handle, C.byref(ptr)))
+        return ptr.value
+
+    def ipc_close(self, ptr):
+        self.lib.qmfb_ipc_close(C.c_void_p(ptr))
+
+    def ipc_free(self, ptr):
+        self.lib.qmfb_ipc_free(C.c_void_p(ptr))
 
     launches_per_half_step = 4  # gram_partial, gram_reduce, wals_solve, sum
+
+
+class _DeviceBuffer:
+    """Zero-copy torch view of a raw device allocation (CUDA array interface)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
 
 
 class ShardedWals:
     """State of one rank.  `csr[side]` = (row_ptr int64 [n+1], col int32 [nnz], val f64 [nnz]) of
     the FULL problem for that orientation, on `device`; the rank keeps only its slice."""
 
-    def __init__(self, nusers, nitems, k, csr_user, csr_item, device, rank=0, world=1, kernels=None):
+    def __init__(self, nusers, nitems, k, csr_user, csr_item, device, rank=0, world=1, kernels=None, exchange="auto"):
         self.n = (int(nusers), int(nitems))
         self.k = int(k)
         self.rank, self.world = rank, world
         self.device = device
         self.kern = kernels if kernels is not None else CudaKernels()
         self.kp = self.kern.padded_k(self.k)
-        self.F = [torch.zeros(self.n[s], self.kp, dtype=torch.float64, device=device) for s in (0, 1)]
+        # exchange of the solved shards: "p2p" = peer stores from the solve kernel into IPC-mapped replicas
+        # (CUDA product path, world > 1), "nccl" = one broadcast per rank after the kernel
+        if exchange == "auto":
+            exchange = "p2p" if (world > 1 and kernels is None and torch.device(device).type == "cuda") else "nccl"
+        self.exchange = exchange
+        self._ipc_own, self._ipc_peers, self.peers = [], [], [(), ()]
+        if exchange == "p2p":
+            self._init_p2p(torch.device(device))
+        else:
+            self.F = [torch.zeros(self.n[s], self.kp, dtype=torch.float64, device=device) for s in (0, 1)]
         self.ranges, self.shard = [], []
         for side, (rp, col, val) in enumerate((csr_user, csr_item)):
             ranges = balanced_row_ranges(rp, world)
@@ -108,6 +148,40 @@ class ShardedWals:
         self.scratch = torch.zeros(2, dtype=torch.int32, device=device)
         self.launches = 0
         self.timing = None  # optional dict of torch.cuda.Event pairs filled by half_step(record=True)
+
+    def _init_p2p(self, device):
+        """Factor replicas as CUDA-IPC allocations; every rank maps every other rank's replicas."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.F, handles = [], []
+        for s in (0, 1):
+            ptr, handle = self.kern.ipc_alloc(idx, self.n[s] * self.kp * 8)
+            self._ipc_own.append(ptr)
+            handles.append(handle)
+            self.F.append(torch.as_tensor(_DeviceBuffer(ptr, (self.n[s], self.kp)), device=device))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles)
+        peers = [[], []]
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            for s in (0, 1):
+                p = self.kern.ipc_open(idx, gathered[r][s])
+                self._ipc_peers.append(p)
+                peers[s].append(p)
+        self.peers = [tuple(peers[0]), tuple(peers[1])]
+
+    def close(self):
+        """Unmap the peers' replicas and free our own (p2p exchange); collective: call on every rank."""
+        if self._ipc_own:
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()
+            for p in self._ipc_peers:
+                self.kern.ipc_close(p)
+            self.F = []
+            for p in self._ipc_own:
+                self.kern.ipc_free(p)
+            self._ipc_own, self._ipc_peers, self.peers = [], [], [(), ()]
 
     def set_factors(self, side, F):
         """F: [n, k] tensor/ndarray (host or device)"""
@@ -130,15 +204,23 @@ class ShardedWals:
             events["solve0"].record()
         # leftData.setFactors(0) (WALSEngine.cpp:170-171) — rows of this shard; the others arrive in step 4
         self.F[side][sh["begin"]:sh["end"]].zero_()
-        self.kern.solve(self.F[side], sh["begin"], self.F[other], self.k, sh["row_ptr"], sh["col"], sh["val"],
-                        sh["order"], self.gram_packed, alpha, lam, self.row_loss, self.loss_sum, self.scratch)
+        if self.exchange == "p2p":
+            self.kern.solve(self.F[side], sh["begin"], self.F[other], self.k, sh["row_ptr"], sh["col"], sh["val"],
+                            sh["order"], self.gram_packed, alpha, lam, self.row_loss, self.loss_sum, self.scratch,
+                            peers=self.peers[side])
+        else:
+            self.kern.solve(self.F[side], sh["begin"], self.F[other], self.k, sh["row_ptr"], sh["col"], sh["val"],
+                            sh["order"], self.gram_packed, alpha, lam, self.row_loss, self.loss_sum, self.scratch)
         if events is not None:
             events["solve1"].record()
         self.launches += self.kern.launches_per_half_step
         if self.world > 1:
-            for r, (b, e) in enumerate(self.ranges[side]):
-                if e > b:
-                    dist.broadcast(self.F[side][b:e], src=r)
+            if self.exchange != "p2p":
+                for r, (b, e) in enumerate(self.ranges[side]):
+                    if e > b:
+                        dist.broadcast(self.F[side][b:e], src=r)
+            # also the cross-rank ordering point of the p2p exchange: it completes on a rank only after every
+            # rank's solve kernel (and with it that rank's peer stores) has completed
             dist.all_reduce(self.loss_sum)
         return self.loss_sum
 

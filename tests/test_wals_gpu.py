@@ -142,6 +142,41 @@ def test_epoch_host_roundtrip(oracle_lib):
     assert abs(loss - lo) <= LOSS_TOL * abs(lo)
 
 
+@pytest.mark.parametrize("k,npeers", [(30, 1), (128, 3), (128, 7), (160, 2)])
+def test_fused_peer_stores_replicate_the_solved_rows(k, npeers):
+    """qmfb_wals_solve_peers_dev: every solved row also lands in row (row_offset + r) of each peer
+    replica (here: further buffers on the same GPU; across GPUs they are IPC-mapped peer memory)"""
+    import torch
+    from qmf_b200 import csr_from_coo
+    from qmf_b200.wals_dist import CudaKernels
+    K = CudaKernels()
+    dev = torch.device("cuda", 0)
+    u, i, v = uniform_dataset(3 * k + 40, 2 * k + 30, 30 * k, 5 + k, id_scale=(1, 1))
+    uids, urp, uci, uv = csr_from_coo(u, i, v)
+    NU, NI, kp = len(uids), int(uci.max()) + 1, K.padded_k(k)
+    Y = torch.zeros(NI, kp, dtype=torch.float64, device=dev)
+    Y[:, :k] = torch.from_numpy(init_factors(NI, k, seed=3)).to(dev)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+    rp, col, val = t(urp, torch.int64), t(uci, torch.int32), t(uv, torch.float64)
+    order = torch.argsort(rp[1:] - rp[:-1], descending=True, stable=True).to(torch.int32)
+    gram = torch.zeros(K.gram_packed_len(k), dtype=torch.float64, device=dev)
+    ws = torch.empty(K.gram_workspace_len(k), dtype=torch.float64, device=dev)
+    K.gram(Y, 0, NI, k, ws, gram)
+    off = 11  # the shard's rows sit at [off, off + NU) of the replicas
+    bufs = [torch.full((NU + 2 * off, kp), -7.0, dtype=torch.float64, device=dev) for _ in range(npeers + 1)]
+    row_loss = torch.zeros(NU, dtype=torch.float64, device=dev)
+    loss, scratch = torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(2, dtype=torch.int32, device=dev)
+    K.solve(bufs[0], off, Y, k, rp, col, val, order, gram, 40.0, 0.05, row_loss, loss, scratch,
+            peers=tuple(b.data_ptr() for b in bufs[1:]))
+    torch.cuda.synchronize()
+    assert int(scratch[1]) == 0
+    ref = bufs[0].cpu().numpy()
+    assert np.all(ref[:off] == -7.0) and np.all(ref[off + NU:] == -7.0) and np.all(ref[off:off + NU, k:] == 0.0)
+    assert np.abs(ref[off:off + NU, :k]).max() > 0
+    for b in bufs[1:]:
+        assert np.array_equal(b.cpu().numpy(), ref)
+
+
 def test_sharded_driver_single_rank_matches_oracle(oracle_lib):
     """the kernel-level ABI (device pointers, caller-owned torch tensors) used by the multi-GPU driver"""
     import torch
