@@ -41,7 +41,10 @@ constexpr int kChunk = 16;   // gathered rows per pipeline stage
 // critical path on the shared FP64 pipe (4 in flight: 27.3 ms on the user-shaped half of C4, 1: 25.3 ms;
 // tools/exp_user.py)
 constexpr int kTU = 1;
-constexpr int kStages = 4;   // ring depth
+#ifndef QMFB_KSTAGES
+#define QMFB_KSTAGES 5
+#endif
+constexpr int kStages = QMFB_KSTAGES;   // ring depth
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers
