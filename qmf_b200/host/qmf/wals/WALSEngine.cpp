@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <random>
+#include <thread>
 
 #include "qmf_b200.h"
 
@@ -38,14 +39,23 @@ void WALSEngine::init(const std::vector<DatasetElem>& dataset) {
   // sorts of the whole dataset.
   qmfb_signals_t* signals = nullptr;
   {
-    std::vector<int64_t> uid(dataset.size()), iid(dataset.size());
-    std::vector<double> val(dataset.size());
-    for (size_t p = 0; p < dataset.size(); ++p) {
-      uid[p] = dataset[p].userId;
-      iid[p] = dataset[p].itemId;
-      val[p] = dataset[p].value;
-    }
-    QMFB_OK_OR_DIE(qmfb_signals_build(config_.device, int64_t(dataset.size()), uid.data(), iid.data(), val.data(), &signals));
+    // struct-of-arrays copy of the dataset, first-touched and filled by all host threads
+    const size_t n = dataset.size();
+    std::unique_ptr<int64_t[]> uid(new int64_t[n]), iid(new int64_t[n]);
+    std::unique_ptr<double[]> val(new double[n]);
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), n / 65536 + 1));
+    std::vector<std::thread> pool;
+    auto fill = [&](size_t t) {
+      for (size_t p = n * t / nthreads, e = n * (t + 1) / nthreads; p < e; ++p) {
+        uid[p] = dataset[p].userId;
+        iid[p] = dataset[p].itemId;
+        val[p] = dataset[p].value;
+      }
+    };
+    for (size_t t = 1; t < nthreads; ++t) pool.emplace_back(fill, t);
+    fill(0);
+    for (auto& th : pool) th.join();
+    QMFB_OK_OR_DIE(qmfb_signals_build(config_.device, int64_t(n), uid.get(), iid.get(), val.get(), &signals));
   }
   int64_t nu = 0, ni = 0;
   QMFB_OK_OR_DIE(qmfb_signals_dims(signals, &nu, &ni, nullptr));
