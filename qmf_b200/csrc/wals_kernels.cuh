@@ -480,7 +480,7 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
     prefetch_idx();
   };
   prefetch_idx();
-  if (mine < lim && mine < base + kAhead) issue_mine();  // prologue: the first kAhead chunks of the row
+  while (mine < lim && mine < base + kAhead) issue_mine();  // prologue: the first kAhead chunks of the row (a warp may own several when kAhead > NWARPS)
 
   QMFB_T(tq1);
   double acc[NT + 3][2];

@@ -40,7 +40,7 @@ def test_wals_binary_matches_reference_binary(tmp_path):
            "--nthreads", "4", "--train_dataset=" + os.path.join(CLI, "train.txt"), "--test_dataset=" + os.path.join(CLI, "test.txt"),
            "--distribution_file=" + os.path.join(CLI, "dist.txt"), "--test_avg_metrics=auc,ap,p@10,r@10", "--test_always",
            "--user_factors=" + uf, "--item_factors=" + itf]
-    r = subprocess.run(cmd, env=dict(os.environ, QMF_LOG_PRECISION="17"), capture_output=True, text=True)
+    r = subprocess.run(cmd, env=dict(os.environ, QMF_LOG_PRECISION="17"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     for mine, ref in ((uf, "ref_user_factors.txt"), (itf, "ref_item_factors.txt")):
         ids, F = read_factors(mine)
@@ -58,7 +58,7 @@ def test_wals_binary_matches_reference_binary(tmp_path):
 
 def test_wals_default_log_format():
     r = subprocess.run([os.path.join(BIN, "wals"), "--nepochs=1", "--nfactors=8", "--seed=5",
-                        "--train_dataset=" + os.path.join(CLI, "train.txt")], capture_output=True, text=True)
+                        "--train_dataset=" + os.path.join(CLI, "train.txt")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert re.search(r"epoch 1: train loss = \d\.\d{1,6}\n", r.stderr)           # ostream default precision
     assert "missing model output filenames" in r.stderr
@@ -80,7 +80,7 @@ def test_bpr_binary_runs_and_learns(tmp_path):
     cmd = [os.path.join(BIN, "bpr"), "--nepochs=12", "--nfactors=16", "--use_biases", "--num_negative_samples=3", "--seed=11",
            "--train_dataset=" + train, "--test_dataset=" + test, "--test_avg_metrics=auc,p@10", "--num_hogwild_threads=8",
            "--user_factors=" + uf, "--item_factors=" + itf]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     losses = [(float(a), float(b)) for a, b in re.findall(r"train loss = (\S+), test loss = (\S+)", r.stderr)]
     assert len(losses) == 12 and losses[-1][0] < 0.45 < losses[0][0] + 0.3 and losses[-1][1] < 0.62
