@@ -20,6 +20,7 @@
 
 namespace qmfb {
 
+constexpr int kBprPrefetch = 3;    // negatives sampled / fetched together per positive pair
 constexpr int kBprMaxPerLane = 8;  // factors per lane: supports nfactors <= 256
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), counter-based: no RNG state in memory ------------------
@@ -84,26 +85,28 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // One SGD step on the triplet (u, i, j) with p_u and q_i held in registers (BPREngine::update).
 // Returns e.  q_j is read from and written back to global memory.
-template <int NPL, bool ATOMIC>
-__device__ __forceinline__ double bpr_step(const BprParams& prm, double (&pu)[NPL], double (&qi)[NPL], double& bi,
-                                           double (&dpu)[NPL], double (&dqi)[NPL], double& dbi, int32_t j, int lane) {
-  double qj[NPL];
-  double* qjp = prm.Q + int64_t(j) * prm.k;
+template <int NPL>
+__device__ __forceinline__ void bpr_load_row(const BprParams& prm, int32_t j, double (&qj)[NPL], double& bj, int lane) {
+  const double* qjp = prm.Q + int64_t(j) * prm.k;
 #pragma unroll
   for (int m = 0; m < NPL; ++m) {
     const int f = lane + 32 * m;
     qj[m] = f < prm.k ? qjp[f] : 0.0;
   }
+  bj = prm.bias != nullptr ? prm.bias[j] : 0.0;
+}
+
+template <int NPL, bool ATOMIC>
+__device__ __forceinline__ double bpr_step(const BprParams& prm, double (&pu)[NPL], double (&qi)[NPL], double& bi,
+                                           double (&dpu)[NPL], double (&dqi)[NPL], double& dbi, int32_t j,
+                                           const double (&qj)[NPL], double bj, int lane) {
+  double* qjp = prm.Q + int64_t(j) * prm.k;
   // x = b_i - b_j + p_u . (q_i - q_j), BPREngine.cpp:222-235
   double part = 0.0;
 #pragma unroll
   for (int m = 0; m < NPL; ++m) part += pu[m] * (qi[m] - qj[m]);
   double x = warp_sum(part);
-  double bj = 0.0;
-  if (prm.bias != nullptr) {
-    bj = prm.bias[j];
-    x += bi - bj;
-  }
+  if (prm.bias != nullptr) x += bi - bj;
   const double e = 1.0 / (1.0 + exp(x));  // lossDerivative, BPREngine.cpp:241-244
   if (prm.bias != nullptr) {  // BPREngine.cpp:189-196
     const double si = prm.lr * (e - prm.bias_lambda * bi);
@@ -156,24 +159,66 @@ __global__ void __launch_bounds__(256) bpr_epoch_kernel(const BprParams prm) {
     double dpu[NPL], dqi[NPL], dbi = 0.0;
 #pragma unroll
     for (int m = 0; m < NPL; ++m) dpu[m] = dqi[m] = 0.0;
-    for (int n = 0; n < prm.num_neg; ++n) {
-      // sampleRandomNegative (BPREngine-inl.h:48-60): uniform item, reject the user's train positives
-      int32_t j = -1;
-      for (int blk = 0; blk < 16 && j < 0; ++blk) {
+    // sampleRandomNegative (BPREngine-inl.h:48-60): uniform item, reject the user's train positives.
+    // The candidates of up to kBprPrefetch negatives are drawn and checked TOGETHER (the binary
+    // searches over the user's positives advance in lockstep: independent loads in flight instead of
+    // one dependent chain per negative) and their rows are fetched together before the sequential
+    // SGD steps - the kernel is latency bound (profiles/r01_bpr_large_ncu.csv: 33 % of the warps
+    // resident, 6.8 warps stalled on memory per issue), not bandwidth bound.
+    auto draw = [&](int n, int first) -> int32_t {  // candidates first, first+1, ... of negative n
+      for (int c = first; c < 64; ++c) {
         uint32_t r[4];
-        rng(uint32_t(p), uint32_t(uint64_t(p) >> 32), uint32_t(n), uint32_t(blk), r);
+        rng(uint32_t(p), uint32_t(uint64_t(p) >> 32), uint32_t(n), uint32_t(c >> 2), r);
+        const int32_t cand = int32_t(__umulhi(r[c & 3], uint32_t(prm.nitems)));
+        if (!bpr_contains(prm.pos_items, lo, hi, cand)) return cand;
+      }
+      return -1;
+    };
+    for (int n0 = 0; n0 < prm.num_neg; n0 += kBprPrefetch) {
+      int32_t js[kBprPrefetch];
+      int64_t l[kBprPrefetch];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int32_t cand = int32_t(__umulhi(r[a], uint32_t(prm.nitems)));
-          if (j < 0 && !bpr_contains(prm.pos_items, lo, hi, cand)) j = cand;
+      for (int a = 0; a < kBprPrefetch; ++a) {
+        uint32_t r[4];
+        rng(uint32_t(p), uint32_t(uint64_t(p) >> 32), uint32_t(n0 + a), 0u, r);
+        js[a] = int32_t(__umulhi(r[0], uint32_t(prm.nitems)));
+        l[a] = lo;
+      }
+      {  // lockstep lower_bound of every candidate in pos_items[lo, hi)
+        int64_t h[kBprPrefetch];
+#pragma unroll
+        for (int a = 0; a < kBprPrefetch; ++a) h[a] = hi;
+        for (int64_t span = hi - lo; span > 0; span >>= 1) {
+#pragma unroll
+          for (int a = 0; a < kBprPrefetch; ++a) {
+            if (l[a] < h[a]) {
+              const int64_t mid = (l[a] + h[a]) >> 1;
+              if (__ldg(prm.pos_items + mid) < js[a]) l[a] = mid + 1; else h[a] = mid;
+            }
+          }
         }
       }
-      if (j < 0) {
-        gave_up = true;
-        continue;
+#pragma unroll
+      for (int a = 0; a < kBprPrefetch; ++a) {
+        if (n0 + a < prm.num_neg) {
+          if (l[a] < hi && __ldg(prm.pos_items + l[a]) == js[a]) js[a] = draw(n0 + a, 1);  // rare: a train positive
+          if (js[a] < 0) gave_up = true;
+        } else {
+          js[a] = -1;
+        }
       }
-      const double e = bpr_step<NPL, true>(prm, pu, qi, bi, dpu, dqi, dbi, j, lane);
-      bad = bad || !isfinite(e);
+      double qj[kBprPrefetch][NPL], bj[kBprPrefetch];
+#pragma unroll
+      for (int a = 0; a < kBprPrefetch; ++a) {
+        if (js[a] >= 0) bpr_load_row<NPL>(prm, js[a], qj[a], bj[a], lane);
+      }
+#pragma unroll
+      for (int a = 0; a < kBprPrefetch; ++a) {
+        if (js[a] >= 0) {
+          const double e = bpr_step<NPL, true>(prm, pu, qi, bi, dpu, dqi, dbi, js[a], qj[a], bj[a], lane);
+          bad = bad || !isfinite(e);
+        }
+      }
     }
 #pragma unroll
     for (int m = 0; m < NPL; ++m) {
@@ -211,7 +256,9 @@ __global__ void bpr_replay_kernel(BprParams prm, const int32_t* __restrict__ tu,
     double dpu[NPL], dqi[NPL], dbi = 0.0;
 #pragma unroll
     for (int m = 0; m < NPL; ++m) dpu[m] = dqi[m] = 0.0;
-    const double e = bpr_step<NPL, false>(prm, pu, qi, bi, dpu, dqi, dbi, j, lane);
+    double qj[NPL], bj;
+    bpr_load_row<NPL>(prm, j, qj, bj, lane);
+    const double e = bpr_step<NPL, false>(prm, pu, qi, bi, dpu, dqi, dbi, j, qj, bj, lane);
     bad = bad || !isfinite(e);
 #pragma unroll
     for (int m = 0; m < NPL; ++m) {
