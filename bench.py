@@ -296,7 +296,7 @@ def run_eval_ours(device=0):
     return {"shape": {"test_users": nu, "nitems": ni, "nfactors": k, "positives_per_user": npos}, "ms": t * 1e3,
             "user_item_scores_per_s": nu * ni / t, "gflops": 2.0 * nu * ni * k / t * 1e-9,
             "note": "exact-order FP64 mul+add (no FMA) so that scores are bit-identical to the reference; 3 launches "
-                    "(2 memsets + eval_rank_kernel)"}
+                    "(2 memsets + eval_rank_kernel, 4 users per CTA)"}
 
 
 # ------------------------------------------------------------------------------------------------

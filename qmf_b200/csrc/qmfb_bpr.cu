@@ -387,7 +387,8 @@ int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double*
   int dev = 0, sms = 148;
   QMFB_CUDA(cudaGetDevice(&dev));
   QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int blocks = int(std::min<int64_t>(nT, int64_t(sms) * 2));
+  const int64_t ngroups = (nT + kEvalGroup - 1) / kEvalGroup;
+  const int blocks = int(std::min<int64_t>(ngroups, int64_t(sms) * 2));
   eval_rank_kernel<<<blocks, kEvalThreads, smem, st>>>(p, int(nT));
   QMFB_CUDA(cudaGetLastError());
   return QMFB_OK;
