@@ -4,7 +4,7 @@
 //   WALSEngine::updateFactorsForOne  qmf/wals/WALSEngine.cpp:266-310   (K2 build, K3 solve, K4 loss)
 //   linearSymmetricSolve / dsysv_    qmf/Matrix.cpp:81-96              (K3)
 //
-// Design (see DESIGN.md §3):
+// Design (see DESIGN.md §4.1):
 //  * FP64 tensor cores: B200 has no tcgen05 FP64 kind; the native FP64 MMA is DMMA.8x8x4
 //    (mma.sync.m8n8k4.f64).  Measured peak 37.1 TFLOP/s (profiles/r01_fp64_peak.txt); the
 //    shared-memory-fed loop below reaches ~35 TFLOP/s in isolation.
@@ -12,14 +12,18 @@
 //    tile-rows w and NT-1-w (NT+1 tiles -> perfectly balanced), accumulators live in registers.
 //  * Factor rows are staged into padded shared memory (row stride KP+4 doubles -> conflict-free
 //    DMMA fragment loads) through an mbarrier-tracked ring, no register staging.  Gathered rows
-//    (solve kernel) use 16-byte cp.async (LDGSTS) issued by all threads: the TMA engine's
+//    (solve kernel) use 16-byte cp.async (LDGSTS), one warp per chunk in rotation: the TMA engine's
 //    outstanding-request window caps a DRAM-resident 1 KB-row gather at ~5 B/clk/SM
 //    (profiles/r01_solve_v1_*: 49 % of warp samples waiting on the full barrier), LDGSTS has no
 //    such cap.  The Gram kernel streams contiguous rows with TMA bulk copies (cp.async.bulk).
-//  * Accumulators start from the Gram tiles; after the build lambda is added and the tiles go to
-//    shared memory, where a blocked right-looking Cholesky (8-wide panels, DMMA trailing
-//    updates, look-ahead on the diagonal tile, b carried as an extra tile column so the forward
-//    solve is free) and a blocked back substitution produce x.  A never leaves the SM.
+//  * Accumulators start from the Gram tiles, b is accumulated as two more DMMA tiles per warp; after
+//    the build lambda is added and the tiles go to shared memory (XOR-swizzled 8x8 tiles: every
+//    operand-fragment load is conflict-free), where a blocked right-looking Cholesky (8-wide panels,
+//    DMMA trailing updates, look-ahead on the diagonal tile, b carried as an extra tile column so the
+//    forward solve is free) and a blocked back substitution produce x.  A never leaves the SM.
+//    (k > 128: wals_big.cuh keeps the tiles in an L2-resident workspace and shares solve_row.)
+//  * Multi-GPU: the solved row is stored to the local replica AND to the peers' replicas (NVLink
+//    peer memory) by the same warps - the all-gather of the half-step is part of this kernel.
 //  * Two persistent CTAs per SM at k=128 (tile storage aliases the staging ring): while one CTA
 //    is in its latency-bound solve phase the other keeps the DMMA pipe busy building.  The solve
 //    phase is written for a short FP64 dependency chain (fraction-free 8x8 pivot block, see
@@ -92,21 +96,12 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // D(8x8) += A(8x4) * B(4x8), FP64.  Lane T holds A[T/4][T%4], B[T%4][T/4], C[T/4][2*(T%4)+{0,1}].
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
-}
-
-// c[m][n] += sum_kk ta[kk][m] * tb[kk][n] for two 8x8 row-major tiles in shared memory
-// (conflict-free: lanes read 32 consecutive doubles per fragment).
-__device__ __forceinline__ void tile_mma_tn(double (&c)[2], const double* ta, const double* tb, int lane, double sa) {
-  const int o = (lane & 3) * 8 + (lane >> 2);
-  dmma(c, sa * ta[o], tb[o]);
-  dmma(c, sa * ta[o + 32], tb[o + 32]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -123,7 +118,6 @@ struct WalsSmem {
   static constexpr int LD = KP + 4;
   static constexpr int NWARPS = NT / 2;
   static constexpr int NTHREADS = NWARPS * 32;  // == 2 * KP
-  static constexpr int NACC = NT + 1;           // tiles per warp (rows w and NT-1-w)
   static constexpr int NTILE_A = NT * (NT + 1) / 2;
   static constexpr int NTILE = NTILE_A + NT;    // + one tile column for b
   static constexpr size_t kStageBytes = size_t(kStages) * kChunk * LD * 8;
