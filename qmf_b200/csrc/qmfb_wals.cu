@@ -223,6 +223,8 @@ struct qmfb_wals {
   int64_t n[2] = {0, 0};
   int k = 0, kp = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // device-to-host copy of the user factors, overlapped with the item half-step
+  cudaEvent_t ev_user = nullptr, ev_copy = nullptr;
   double* F[2] = {nullptr, nullptr};
   int64_t row_begin[2] = {0, 0}, nrows[2] = {0, 0}, nnz[2] = {0, 0};
   int64_t* row_ptr[2] = {nullptr, nullptr};
@@ -254,6 +256,9 @@ static int wals_release(qmfb_wals* h) {
   for (auto& e : h->ev) {
     if (e) cudaEventDestroy(e);
   }
+  if (h->ev_user) cudaEventDestroy(h->ev_user);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return QMFB_OK;
@@ -272,6 +277,9 @@ int qmfb_wals_create(int device, int64_t nusers, int64_t nitems, int nfactors, q
   h->kp = kp;
   int rc = [&]() -> int {
     QMFB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    QMFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    QMFB_CUDA(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
+    QMFB_CUDA(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
     for (int s = 0; s < 2; ++s) {
       QMFB_CUDA(cudaMalloc(&h->F[s], size_t(h->n[s]) * kp * sizeof(double)));
       QMFB_CUDA(cudaMemsetAsync(h->F[s], 0, size_t(h->n[s]) * kp * sizeof(double), h->stream));
@@ -463,11 +471,17 @@ int qmfb_wals_epoch_host(qmfb_wals_t* h, double alpha, double lambda, const doub
   int32_t err_user[2] = {0, 0};
   QMFB_CUDA(cudaMemcpyAsync(err_user, h->scratch, sizeof(err_user), cudaMemcpyDeviceToHost, h->stream));
   if (user_factors_out) {
+    // the user factors are final after the user half-step: their copy to the host runs on a second
+    // stream underneath the item half-step (which only reads them)
+    QMFB_CUDA(cudaEventRecord(h->ev_user, h->stream));
+    QMFB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_user, 0));
     QMFB_CUDA(cudaMemcpy2DAsync(user_factors_out, size_t(h->k) * 8, h->F[0], size_t(h->kp) * 8, size_t(h->k) * 8,
-                                size_t(h->n[0]), cudaMemcpyDeviceToHost, h->stream));
+                                size_t(h->n[0]), cudaMemcpyDeviceToHost, h->copy_stream));
+    QMFB_CUDA(cudaEventRecord(h->ev_copy, h->copy_stream));
   }
   rc = wals_half_step_async(h, QMFB_SIDE_ITEM, alpha, lambda);
   if (rc) return rc;
+  if (user_factors_out) QMFB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
   if (item_factors_out) {
     QMFB_CUDA(cudaMemcpy2DAsync(item_factors_out, size_t(h->k) * 8, h->F[1], size_t(h->kp) * 8, size_t(h->k) * 8,
                                 size_t(h->n[1]), cudaMemcpyDeviceToHost, h->stream));
