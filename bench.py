@@ -405,11 +405,7 @@ def run_ours(args, cfg, workload):
         loss_host = torch.empty(1, dtype=torch.float64).pin_memory()
 
         def e2e_step():
-            sw.F[1][:, :k].copy_(item_in, non_blocking=True)
-            l = sw.epoch(ALPHA, LAMBDA)
-            user_out.copy_(sw.F[0][ub:ue, :k], non_blocking=True)
-            item_out.copy_(sw.F[1][ib:ie, :k], non_blocking=True)
-            loss_host.copy_(l, non_blocking=True)
+            sw.epoch_host(ALPHA, LAMBDA, item_in, user_out, item_out, loss_host)
 
         if world == 1:
             # through the engine-level C ABI (qmfb_wals_epoch_host), the call qmf::WALSEngine binds
@@ -445,7 +441,7 @@ def run_ours(args, cfg, workload):
             e2e_ms = float(t.item()) / args.steps
             e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "nnz/s", "h2d_bytes_per_step": world * ni * k * 8,
                    "d2h_bytes_per_step": (nu + ni) * k * 8 + 8 * world, "ms_per_step": e2e_ms,
-                   "api": "ShardedWals.epoch with pinned host factors in/out on every rank (CUDA events, max over ranks)"}
+                   "api": "ShardedWals.epoch_host: pinned host factors in/out on every rank (CUDA events, max over ranks)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -231,6 +231,29 @@ class ShardedWals:
         loss = self.half_step(1, alpha, lam, events[1] if events else None)
         return loss / self.n[0] / self.n[1]
 
+    def epoch_host(self, alpha, lam, item_in, user_out, item_out, loss_out=None):
+        """One epoch with (pinned) host buffers: the item factors come from `item_in` [nitems, k], this
+        rank's solved user / item rows go to `user_out` / `item_out`.  The copy of the user rows runs on
+        a side stream underneath the item half-step (which only reads them).  Asynchronous."""
+        k = self.k
+        ub, ue = self.shard[0]["begin"], self.shard[0]["end"]
+        ib, ie = self.shard[1]["begin"], self.shard[1]["end"]
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        self.F[1][:, :k].copy_(item_in, non_blocking=True)
+        self.half_step(0, alpha, lam)
+        self._copy_stream.wait_stream(main)
+        with torch.cuda.stream(self._copy_stream):
+            user_out.copy_(self.F[0][ub:ue, :k], non_blocking=True)
+        loss = self.half_step(1, alpha, lam)
+        item_out.copy_(self.F[1][ib:ie, :k], non_blocking=True)
+        loss = loss / self.n[0] / self.n[1]
+        if loss_out is not None:
+            loss_out.copy_(loss, non_blocking=True)
+        main.wait_stream(self._copy_stream)
+        return loss
+
     def check_error(self):
         if int(self.scratch[1].item()) != 0:
             raise RuntimeError("normal equations not positive definite (reference: dsysv failed, qmf/Matrix.cpp:94)")
