@@ -45,6 +45,12 @@ constexpr int kChunk = 16;   // gathered rows per pipeline stage
 // critical path on the shared FP64 pipe (4 in flight: 27.3 ms on the user-shaped half of C4, 1: 25.3 ms;
 // tools/exp_user.py)
 constexpr int kTU = 1;
+#ifndef QMFB_B_DFMA
+// 1: b = sum_s (1 + alpha r_s) y_s accumulated with DFMA, every warp 16 columns (8 LDS + 8 DFMA per lane and
+//    chunk); 0: as two extra DMMA tiles per warp (7/8 of their columns are zeros: +12 % tensor-pipe time).
+//    Measured on the item-shaped half of C4: 14.17 ms vs 15.03 ms (tools/exp_user.py); user half unchanged.
+#define QMFB_B_DFMA 1
+#endif
 #ifndef QMFB_KSTAGES
 #define QMFB_KSTAGES 5
 #endif
@@ -488,6 +494,9 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
     acc[t][1] = g.y;
   }
   QMFB_T(tq2);
+#if QMFB_B_DFMA
+  double bacc = 0.0;
+#endif
   for (int c = 0; c < nch; ++c) {
     const uint32_t gc = base + c, st = gc % kStages;
     // the stage refilled here was consumed TWO chunks ago: its empty barrier completed long ago
@@ -499,7 +508,17 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
     QMFB_T(tb2);
     const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
     const double* w8 = wts + st * 2 * kChunk;
+#if QMFB_B_DFMA
+    {  // b: this warp's 16 columns, half of the chunk's rows per half-warp (conflict-free 128-byte segments)
+      const double* pb = sb + (lane >> 4) * SM::LD + warp * 16 + (lane & 15);
+      const double* pw = w8 + kChunk + (lane >> 4);
+#pragma unroll
+      for (int j = 0; j < kChunk / 2; ++j) bacc = fma(pw[2 * j], pb[2 * j * SM::LD], bacc);
+    }
+    chunk_mma_dispatch<NT, 0, false>(warp, acc, sb, w8, lane);
+#else
     chunk_mma_dispatch<NT, 0, true>(warp, acc, sb, w8, lane);
+#endif
     QMFB_T(tb3);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
@@ -529,8 +548,18 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
     }
     *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(I, J)) * 64 + tile_acc_off(lane)) = make_double2(v0, v1);
   }
+#if QMFB_B_DFMA
+  bacc += __shfl_xor_sync(0xffffffffu, bacc, 16);  // lane l (and l + 16) now holds b(16 * warp + l % 16)
+#pragma unroll
+  for (int tt = 0; tt < 2; ++tt) {  // b column tiles 2 * warp + tt: column 0 = b, other columns 0
+    const double v = __shfl_sync(0xffffffffu, bacc, 8 * tt + (lane >> 2));
+    *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(2 * warp + tt, NT)) * 64 + tile_acc_off(lane)) =
+      make_double2((lane & 3) == 0 ? v : 0.0, 0.0);
+  }
+#else
   *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(warp, NT)) * 64 + tile_acc_off(lane)) = make_double2(acc[NT + 1][0], acc[NT + 1][1]);
   *reinterpret_cast<double2*>(tiles + size_t(SM::tidx(NT - 1 - warp, NT)) * 64 + tile_acc_off(lane)) = make_double2(acc[NT + 2][0], acc[NT + 2][1]);
+#endif
   QMFB_T(tq6);
   QMFB_ACC(16, tq0, tq1);
   QMFB_ACC(17, tq1, tq2);
