@@ -23,7 +23,7 @@ def _setup(nu, ni, nnz, k, seed, dup=0):
     return h, (urp, uci, uv), (irp, ici, iv), len(uids), len(iids)
 
 
-@pytest.mark.parametrize("n,k", [(1, 30), (17, 5), (1000, 30), (5000, 64), (3001, 100), (20000, 128), (40, 1),
+@pytest.mark.parametrize("n,k", [(1, 30), (17, 5), (1000, 30), (5000, 64), (3001, 100), (20000, 128), (40, 1), (2500, 80), (999, 96),
                                  (3000, 129), (777, 160), (5000, 200), (4097, 256)])
 def test_gram_matches_oracle(oracle_lib, n, k):
     from qmf_b200 import WalsEngineHandle
@@ -39,6 +39,7 @@ def test_gram_matches_oracle(oracle_lib, n, k):
 
 @pytest.mark.parametrize("nu,ni,nnz,k,dup", [(300, 200, 6000, 30, 0), (200, 150, 4000, 64, 25), (400, 300, 12000, 128, 0),
                                               (260, 210, 5000, 100, 0), (50, 40, 300, 8, 5),
+                                              (240, 200, 5000, 80, 0), (250, 200, 5000, 96, 3), (100, 90, 2000, 33, 0),
                                               # 128 < k <= 256: workspace-resident tiles (wals_big.cuh)
                                               (420, 340, 9000, 160, 0), (600, 520, 16000, 256, 10), (450, 400, 9000, 200, 0)])
 def test_epochs_match_oracle(oracle_lib, nu, ni, nnz, k, dup):
