@@ -21,7 +21,7 @@ def _planted(nu, ni, npairs, seed, rank=6):
 
 
 @pytest.mark.parametrize("k,biases", [(30, True), (30, False), (64, True), (100, False), (7, True), (128, True),
-                                      (160, False), (256, True)])
+                                      (160, False), (256, True), (96, True), (200, False)])
 def test_update_triplets_match_oracle(oracle_lib, k, biases):
     from qmf_b200.bpr import BprEngineHandle
     import oracle
@@ -130,7 +130,8 @@ def test_hogwild_epochs_learn_planted_preferences(oracle_lib):
     assert auc_gpu > 0.7 and abs(auc_gpu - auc_cpu) < 0.03, (auc_gpu, auc_cpu)
 
 
-@pytest.mark.parametrize("nu,ni,k,biases", [(50, 333, 30, True), (20, 1000, 64, False), (8, 77, 128, True), (5, 40, 3, False)])
+@pytest.mark.parametrize("nu,ni,k,biases", [(50, 333, 30, True), (20, 1000, 64, False), (8, 77, 128, True), (5, 40, 3, False),
+                                            (6, 90, 200, True), (1, 17, 16, False), (9, 2100, 17, True)])
 def test_rank_statistics_bit_exact(oracle_lib, nu, ni, k, biases):
     """Scores bit-identical to Engine::computeTestScores, therefore identical ranking: AUC (exact
     replay), AP, P@k and R@k must EQUAL the oracle's values, ties included."""
