@@ -4,6 +4,7 @@
 #include "wals_big.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 #include <vector>
 
@@ -31,8 +32,26 @@ static int launch_gram(cudaStream_t st, const double* Y, int64_t ldy, int64_t r0
   return QMFB_OK;
 }
 
+// Stream-ordered scratch (cudaMallocAsync) comes from the device's default memory pool, which by
+// default gives freed memory back to the driver at the next synchronisation: every call would then pay
+// a real allocation.  Keep the pool's memory cached (once per device).
+static int keep_pool_cached() {
+  static bool done[64] = {false};
+  int dev = 0;
+  QMFB_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !done[dev]) {
+    cudaMemPool_t pool;
+    QMFB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;
+    QMFB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done[dev] = true;
+  }
+  return QMFB_OK;
+}
+
 template <int NT>
 static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_sum, int32_t* scratch) {
+  if (int rc = keep_pool_cached()) return rc;
   using SM = WalsSmem<NT>;
   static int grid_cap = 0;
   if (grid_cap == 0) {
@@ -47,8 +66,27 @@ static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_su
   QMFB_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(int32_t), st));
   if (prm.nrows > 0) {
     const int grid = int(std::min<int64_t>(grid_cap, prm.nrows));
-    wals_solve_kernel<NT><<<grid, SM::NTHREADS, SM::kBytes, st>>>(prm);
-    QMFB_CUDA(cudaGetLastError());
+    // extremely long rows at the head of `order` are summed by many CTAs ahead of the solve kernel
+    // (two empty launches when there is none); stream-ordered scratch, freed after the kernel
+    static bool long_configured = false;
+    if (!long_configured) {
+      QMFB_CUDA(cudaFuncSetAttribute(long_row_partial_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+      long_configured = true;
+    }
+    constexpr int kLen = LongRow<NT>::kLen;
+    double* long_buf = nullptr;
+    QMFB_CUDA(cudaMallocAsync(&long_buf, size_t(kLongMax) * (kLongParts + 1) * kLen * sizeof(double), st));
+    LongRowParams lp{prm.Y, prm.ldy, prm.row_ptr, prm.col, prm.val, prm.order, prm.nrows, prm.alpha, long_buf,
+                     long_buf + size_t(kLongMax) * kLongParts * kLen};
+    long_row_partial_kernel<NT><<<dim3(kLongParts, kLongMax), SM::NTHREADS, SM::kBytes, st>>>(lp);
+    long_row_reduce_kernel<NT><<<dim3((kLen + 255) / 256, kLongMax), 256, 0, st>>>(lp);
+    SolveParams run = prm;
+    static const bool no_long = getenv("QMFB_NO_LONG_ROWS") != nullptr;  // measurement switch: ignore the sums
+    run.long_sum = no_long ? nullptr : lp.sum;
+    wals_solve_kernel<NT><<<grid, SM::NTHREADS, SM::kBytes, st>>>(run);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(long_buf, st);
+    QMFB_CUDA(e);
   }
   sum_kernel<<<1, 1024, 0, st>>>(prm.row_loss, prm.nrows, loss_sum);
   QMFB_CUDA(cudaGetLastError());
@@ -84,6 +122,7 @@ static int launch_solve_big(cudaStream_t st, const SolveParams& prm, double* los
     QMFB_CUDA(cudaGetDevice(&dev));
     QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  if (int rc = keep_pool_cached()) return rc;
   QMFB_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(int32_t), st));
   if (prm.nrows > 0) {
     const int grid = int(std::min<int64_t>(sms, prm.nrows));
@@ -196,7 +235,7 @@ int qmfb_wals_solve_peers_dev(void* stream, double* X, int64_t ldx, int64_t row_
     return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_dev: bad argument");
   }
   SolveParams prm{X, ldx, row_offset, Y, ldy, k, row_ptr, col, val, order, int(nrows), gram_packed, alpha, lambda,
-                  row_loss, scratch + 1, npeers, {}};
+                  row_loss, scratch + 1, npeers, {}, nullptr};
   for (int p = 0; p < npeers; ++p) {
     if (!peer_X[p]) return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_peers_dev: null peer pointer %d", p);
     prm.peerX[p] = peer_X[p];
@@ -433,7 +472,8 @@ static int wals_half_step_async(qmfb_wals* h, int side, double alpha, double lam
                            h->row_loss, h->loss_sum, h->scratch);
   if (rc) return rc;
   QMFB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-  h->launches += 4;
+  // gram_partial, gram_reduce, [long_row_partial, long_row_reduce (k <= 128)], wals_solve, sum
+  h->launches += (h->nrows[side] > 0 && h->kp <= 128) ? 6 : 4;
   return QMFB_OK;
 }
 

@@ -305,6 +305,137 @@ __global__ void gram_unpack_kernel(const double* __restrict__ packed, int k, dou
 }
 
 // ------------------------------------------------------------------------------------------
+// Extremely long rows (a blockbuster item): a row is normally built by ONE CTA, so a single row of
+// several hundred thousand entries would be the tail of its half-step (and of every rank's, multi-GPU).
+// The kLongMax longest rows (the head of `order`) that have >= kLongRow entries are therefore built
+// ahead of the solve kernel by kLongParts CTAs each - the Gram kernel's scheme on gathered, weighted
+// rows - and reduced in a fixed order; the solve kernel then starts such a row from
+// Gram + that sum and skips its own gather loop.  Rows below the threshold cost two empty launches.
+// ------------------------------------------------------------------------------------------
+constexpr int kLongMax = 16;          // candidate rows: positions [0, kLongMax) of `order`
+constexpr int kLongParts = 64;        // CTAs per long row
+constexpr int64_t kLongRow = 32768;   // entries
+
+template <int NT>
+struct LongRow {
+  static constexpr int kLen = WalsSmem<NT>::NTILE_A * 64 + WalsSmem<NT>::KP + 8;  // tiles | b | sum of (1 + alpha r), padded
+};
+
+struct LongRowParams {
+  const double* Y;
+  int64_t ldy;
+  const int64_t* row_ptr;
+  const int32_t* col;
+  const double* val;
+  const int32_t* order;
+  int nrows;
+  double alpha;
+  double* partial;  // [kLongMax][kLongParts][kLen]
+  double* sum;      // [kLongMax][kLen]
+};
+
+template <int NT>
+__global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) long_row_partial_kernel(const LongRowParams prm) {
+  using SM = WalsSmem<NT>;
+  const int r = blockIdx.y;
+  if (r >= prm.nrows) return;
+  const int row = prm.order[r];
+  const int64_t p0 = prm.row_ptr[row], p1 = prm.row_ptr[row + 1];
+  if (p1 - p0 < kLongRow) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
+  double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
+  uint64_t* empty = full + kStages;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], SM::NWARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int64_t n = p1 - p0;
+  const int64_t s0 = p0 + n * blockIdx.x / gridDim.x, s1 = p0 + n * (blockIdx.x + 1) / gridDim.x;
+  const int nch = int((s1 - s0 + kChunk - 1) / kChunk);
+  double csum = 0.0;
+
+  auto issue = [&](int c) {  // warp 0 only: one TMA bulk copy per gathered row
+    const uint32_t st = c % kStages;
+    if (c >= kStages) mbar_wait(&empty[st], ((c / kStages) & 1u) ^ 1u);
+    const int64_t p = s0 + int64_t(c) * kChunk + lane;
+    const bool valid = lane < kChunk && p < s1;
+    const double v = valid ? prm.val[p] : 0.0;
+    const int32_t src = valid ? prm.col[p] : 0;
+    if (lane < kChunk) {
+      const double wb = valid ? 1.0 + prm.alpha * v : 0.0;        // WALSEngine.cpp:280
+      wts[st * 2 * kChunk + lane] = valid ? prm.alpha * v : 0.0;  // WALSEngine.cpp:282
+      wts[st * 2 * kChunk + kChunk + lane] = wb;
+      csum += wb;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(&full[st], uint32_t(kChunk) * SM::KP * 8);
+    __syncwarp();
+    if (lane < kChunk) bulk_g2s(stagebuf + (size_t(st) * kChunk + lane) * SM::LD, prm.Y + int64_t(src) * prm.ldy, SM::KP * 8, &full[st]);
+  };
+
+  double acc[NT + 3][2];
+#pragma unroll
+  for (int t = 0; t < NT + 3; ++t) acc[t][0] = acc[t][1] = 0.0;
+  double bacc = 0.0;
+  if (warp == 0) {
+    for (int c = 0; c < nch && c < kStages - 1; ++c) issue(c);
+  }
+  for (int c = 0; c < nch; ++c) {
+    const uint32_t st = c % kStages;
+    if (warp == 0 && c + kStages - 1 < nch) issue(c + kStages - 1);
+    mbar_wait(&full[st], (c / kStages) & 1u);
+    const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
+    const double* w8 = wts + st * 2 * kChunk;
+    {
+      const double* pb = sb + (lane >> 4) * SM::LD + warp * 16 + (lane & 15);
+      const double* pw = w8 + kChunk + (lane >> 4);
+#pragma unroll
+      for (int j = 0; j < kChunk / 2; ++j) bacc = fma(pw[2 * j], pb[2 * j * SM::LD], bacc);
+    }
+    chunk_mma_dispatch<NT, 0, false>(warp, acc, sb, w8, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+  double* out = prm.partial + (size_t(r) * kLongParts + blockIdx.x) * LongRow<NT>::kLen;
+#pragma unroll
+  for (int t = 0; t <= NT; ++t) {
+    int I, J;
+    acc_tile<NT>(warp, t, I, J);
+    *reinterpret_cast<double2*>(out + size_t(SM::gidx(I, J)) * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
+  }
+  bacc += __shfl_xor_sync(0xffffffffu, bacc, 16);
+  if (lane < 16) out[SM::NTILE_A * 64 + warp * 16 + lane] = bacc;
+  if (warp == 0) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+    if (lane == 0) out[SM::NTILE_A * 64 + SM::KP] = csum;
+  }
+}
+
+// sum[r][t] = sum over the kLongParts partials of long row r, fixed order (deterministic)
+template <int NT>
+__global__ void long_row_reduce_kernel(const LongRowParams prm) {
+  const int r = blockIdx.y;
+  if (r >= prm.nrows) return;
+  const int row = prm.order[r];
+  if (prm.row_ptr[row + 1] - prm.row_ptr[row] < kLongRow) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int kLen = LongRow<NT>::kLen;
+  if (t >= kLen) return;
+  const double* p = prm.partial + size_t(r) * kLongParts * kLen + t;
+  double s = 0.0;
+  for (int b = 0; b < kLongParts; ++b) s += p[size_t(b) * kLen];
+  prm.sum[size_t(r) * kLen + t] = s;
+}
+
+// ------------------------------------------------------------------------------------------
 // fused per-row kernel
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 15;  // other ranks of one box
@@ -330,6 +461,7 @@ struct SolveParams {
   // (same ldx / row_offset), instead of a separate collective after the kernel.
   int npeers;
   double* peerX[kMaxPeers];
+  const double* long_sum;  // [kLongMax][LongRow<NT>::kLen] prebuilt sums of the extremely long rows, or nullptr
 };
 
 // Store the solved row (KP doubles in shared memory) to X and to every peer replica.  Target t is
@@ -431,7 +563,9 @@ template <int NT>
 __device__ __forceinline__ void build_row(unsigned char* smem, const double* __restrict__ Y, int64_t ldy,
                                           const int32_t* __restrict__ col, const double* __restrict__ val,
                                           const double* __restrict__ gram, double alpha, double lambda, int k,
-                                          int64_t p0, int64_t p1, uint32_t base) {
+                                          int64_t p0, int64_t p1, uint32_t base, const double* __restrict__ lsrc) {
+  // lsrc != nullptr: an extremely long row whose sum over its entries was built ahead by
+  // long_row_partial_kernel (then p1 == p0 here: no gather loop, start from Gram + that sum)
   using SM = WalsSmem<NT>;
   double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
   double* tiles = reinterpret_cast<double*>(smem + SM::kOffTiles);
@@ -492,10 +626,16 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
     const double2 g = *reinterpret_cast<const double2*>(gram + size_t(SM::gidx(I, J)) * 64 + lane * 2);
     acc[t][0] = g.x;
     acc[t][1] = g.y;
+    if (lsrc != nullptr) {
+      const double2 l = *reinterpret_cast<const double2*>(lsrc + size_t(SM::gidx(I, J)) * 64 + lane * 2);
+      acc[t][0] += l.x;
+      acc[t][1] += l.y;
+    }
   }
+  if (lsrc != nullptr && warp == 0 && lane == 0) csum += lsrc[SM::NTILE_A * 64 + SM::KP];
   QMFB_T(tq2);
 #if QMFB_B_DFMA
-  double bacc = 0.0;
+  double bacc = (lsrc != nullptr && lane < 16) ? lsrc[SM::NTILE_A * 64 + warp * 16 + lane] : 0.0;
 #endif
   for (int c = 0; c < nch; ++c) {
     const uint32_t gc = base + c, st = gc % kStages;
@@ -794,8 +934,12 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       if (sn < prm.nrows) nrow = __ldg(prm.order + sn);
     }
     QMFB_T(tp0);
-    build_row<NT>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k, cs->p0, cs->p1,
-                  cs->base);
+    // an extremely long row at the head of `order` was summed ahead of this kernel: no gather loop
+    const int opos = slot_of(it);
+    const bool is_long = prm.long_sum != nullptr && opos < kLongMax && (cs->p1 - cs->p0) >= kLongRow;
+    const int64_t bp1 = is_long ? cs->p0 : cs->p1;
+    build_row<NT>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k, cs->p0, bp1, cs->base,
+                  is_long ? prm.long_sum + size_t(opos) * LongRow<NT>::kLen : nullptr);
     QMFB_T(tp1);
     QMFB_ACC(0, tp0, tp1);
     int64_t np0 = 0, np1 = 0;
@@ -831,7 +975,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       ns->row = nrow;
       ns->p0 = np0;
       ns->p1 = np1;
-      ns->base = cs->base + uint32_t((cs->p1 - cs->p0 + kChunk - 1) / kChunk);
+      ns->base = cs->base + uint32_t((bp1 - cs->p0 + kChunk - 1) / kChunk);
     }
     ++it;
     __syncthreads();  // tiles / xvec / bcopy free again, next row slot visible

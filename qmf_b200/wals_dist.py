@@ -96,7 +96,7 @@ class CudaKernels:
     def ipc_free(self, ptr):
         self.lib.qmfb_ipc_free(C.c_void_p(ptr))
 
-    launches_per_half_step = 4  # gram_partial, gram_reduce, wals_solve, sum
+    launches_per_half_step = 6  # gram_partial, gram_reduce, long_row_partial, long_row_reduce, wals_solve, sum
 
 
 class _DeviceBuffer:

@@ -240,3 +240,36 @@ def test_full_size_properties_c3():
         assert np.abs((B + lam * np.eye(k)) @ x - b).max() <= 1e-10 * np.abs(b).max(), r
         want = (1 + alpha * w).sum() + x @ B @ x - 2 * x @ b
         assert abs(rl[r] - want) <= 1e-11 * abs(want), (r, rl[r], want)
+
+
+def test_extremely_long_row_is_built_by_many_ctas(oracle_lib):
+    """one item with > kLongRow (32768) ratings: long_row_partial/reduce kernels + the solve kernel's
+    no-gather path must give the oracle's factors and loss; the user side (no long row) is unaffected"""
+    from qmf_b200 import WalsEngineHandle, csr_from_coo
+    rng = np.random.default_rng(99)
+    nu, ni, k = 60000, 200, 64   # nu, ni >= 2k: well-conditioned Gram matrices
+    # item 7 is rated by 50 000 distinct users, everything else is sparse
+    u_long = rng.choice(nu, size=50000, replace=False)
+    u_rest = rng.integers(0, nu, size=120000)
+    i_rest = rng.integers(0, ni, size=120000)
+    u = np.concatenate([u_long, u_rest]).astype(np.int64)
+    i = np.concatenate([np.full(50000, 7), i_rest]).astype(np.int64)
+    cells = np.unique(u * ni + i)
+    u, i = cells // ni, cells % ni
+    v = rng.integers(1, 6, size=len(cells)).astype(np.float64)
+    uids, urp, uci, uv = csr_from_coo(u, i, v)
+    iids, irp, ici, iv = csr_from_coo(i, u, v)
+    NU, NI = len(uids), len(iids)
+    assert np.diff(irp).max() >= 50000
+    h = WalsEngineHandle(NU, NI, k)
+    h.set_csr(0, urp, uci, uv)
+    h.set_csr(1, irp, ici, iv)
+    Y0 = init_factors(NI, k, seed=5)
+    h.set_factors(1, Y0)
+    X, Y = np.zeros((NU, k)), Y0.copy()
+    lu = h.half_step(0, 40.0, 0.05)
+    li = h.half_step(1, 40.0, 0.05)
+    lu_o = oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, urp, uci, uv, 40.0, 0.05, NU, NI, 16)
+    li_o = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, irp, ici, iv, 40.0, 0.05, NU, NI, 16)
+    assert rel_err(h.get_factors(0), X) < FACTOR_TOL and rel_err(h.get_factors(1), Y) < FACTOR_TOL
+    assert abs(lu - lu_o) <= LOSS_TOL * abs(lu_o) and abs(li - li_o) <= LOSS_TOL * abs(li_o)
