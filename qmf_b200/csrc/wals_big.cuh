@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(WalsSmemBig<NT>::NTHREADS, 1) wals_solve_big_k
       store_solved_row(prm, xvec, prm.row_offset + row, SM::KP, warp - 1, lane, 0, SM::NWARPS - 1);
     }
   }
+  if (prm.npeers > 0) __threadfence_system();
 }
 
 }  // namespace qmfb

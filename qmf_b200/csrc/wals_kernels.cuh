@@ -986,6 +986,9 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
     if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[15], 1ull);
 #endif
   }
+  // peer replicas: make this thread's NVLink stores visible system-wide before it retires (kernel
+  // completion implies it; stated explicitly because other ranks read the rows right after the next collective)
+  if (prm.npeers > 0) __threadfence_system();
 }
 
 // deterministic sum of n doubles (fixed strided order + fixed tree), single block
