@@ -192,6 +192,21 @@ int main() {
     EXPECT(!qmf::DatasetReader::parseLine("", "", e));
     EXPECT(!qmf::DatasetReader::parseLine("1 x 3", "1 x 3" + 5, e));
     EXPECT(!qmf::DatasetReader::parseLine("1 2 .", "1 2 ." + 5, e));
+    {  // embedded NUL bytes end the line for sscanf (it sees the C string): same verdicts and values
+#define QMF_LIT(x) std::string(x, sizeof(x) - 1)
+      const std::string cases[] = {QMF_LIT("1 2 3\0junk"), QMF_LIT("1 2\0 3"), QMF_LIT("1 2 3.\0005"), QMF_LIT("1\0 2 3"),
+                                   QMF_LIT("7 8 9e\0002")};
+#undef QMF_LIT
+      for (const auto& c : cases) {
+        long long u = 0, i = 0;
+        double w = 0.0;
+        const bool want = std::sscanf(c.c_str(), "%lld %lld %lf", &u, &i, &w) == 3;
+        qmf::DatasetElem g;
+        const bool got = qmf::DatasetReader::parseLine(c.data(), c.data() + c.size(), g);
+        EXPECT(want == got);
+        if (want && got) EXPECT(g.userId == u && g.itemId == i && std::memcmp(&g.value, &w, sizeof w) == 0);
+      }
+    }
     std::remove(path.c_str());
   }
   // averaging order of Metric::compute(labels, scores, parallel)

@@ -126,8 +126,9 @@ inline bool parseDouble(const char*& p, const char* e, double& out) {
 }  // namespace
 
 bool DatasetReader::parseLine(const char* b, const char* e, DatasetElem& elem) {
-  // sscanf works on the C string: an embedded NUL ends the line
-  if (const void* z = std::memchr(b, 0, size_t(e - b))) e = static_cast<const char*>(z);
+  // sscanf works on the C string: an embedded NUL ends the line.  No pre-scan is needed for that: a NUL
+  // is neither white space nor part of a number, so every scanner below stops at it exactly like sscanf,
+  // and the strtod fallback works on a NUL-terminated copy.
   const char* p = b;
   int64_t u, i;
   double w;
