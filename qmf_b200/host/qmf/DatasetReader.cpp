@@ -49,16 +49,20 @@ inline bool parseInt64(const char*& p, const char* e, int64_t& out) {
     neg = *p == '-';
     ++p;
   }
-  if (p >= e || *p < '0' || *p > '9') return false;
+  if (p >= e || unsigned(*p - '0') > 9u) return false;
   uint64_t v = 0;
-  bool overflow = false;
-  for (; p < e && *p >= '0' && *p <= '9'; ++p) {
-    const uint64_t d = uint64_t(*p - '0');
-    if (v > (UINT64_MAX - d) / 10) overflow = true;
-    if (!overflow) v = v * 10 + d;
+  int nd = 0;
+  for (; p < e && unsigned(*p - '0') <= 9u && nd < 18; ++p, ++nd) v = v * 10 + uint64_t(*p - '0');  // 18 digits cannot overflow
+  if (p < e && unsigned(*p - '0') <= 9u) {  // longer: continue with overflow checks
+    bool overflow = false;
+    for (; p < e && unsigned(*p - '0') <= 9u; ++p) {
+      const uint64_t d = uint64_t(*p - '0');
+      if (v > (UINT64_MAX - d) / 10) overflow = true;
+      if (!overflow) v = v * 10 + d;
+    }
+    const uint64_t lim = neg ? uint64_t(LLONG_MAX) + 1 : uint64_t(LLONG_MAX);
+    if (overflow || v > lim) v = lim;
   }
-  const uint64_t lim = neg ? uint64_t(LLONG_MAX) + 1 : uint64_t(LLONG_MAX);
-  if (overflow || v > lim) v = lim;
   out = neg ? int64_t(0 - v) : int64_t(v);
   return true;
 }
