@@ -50,6 +50,15 @@ def test_no_cpu_fallback_without_a_device():
     assert rc == -2 and "failed" in capi.last_error()        # QMFB_ERR_CUDA, loud
     rc = capi.lib.qmfb_bpr_create(0, 10, 10, 8, 0, C.byref(h))
     assert rc == -2
+    # ingest and the shareable replicas: same contract
+    u = np.array([1, 2, 3], np.int64)
+    rc = capi.lib.qmfb_signals_build(0, 3, u, u, np.ones(3), C.byref(h))
+    assert rc == -2 and "failed" in capi.last_error()
+    rc = capi.lib.qmfb_ipc_alloc(0, 1024, C.byref(h), C.create_string_buffer(64))
+    assert rc == -2
+    with pytest.raises(capi.QmfbError):
+        from qmf_b200.wals import Signals
+        Signals(u, u, np.ones(3))
     with pytest.raises(capi.QmfbError):
         from qmf_b200.wals import WalsEngineHandle
         WalsEngineHandle(4, 4, 8)
