@@ -120,13 +120,14 @@ class ShardedWals:
         self.kp = self.kern.padded_k(self.k)
         # exchange of the solved shards: "p2p" = peer stores from the solve kernel into IPC-mapped replicas
         # (CUDA product path, world > 1), "nccl" = one broadcast per rank after the kernel
-        if exchange == "auto":
+        auto = exchange == "auto"
+        if auto:
             exchange = "p2p" if (world > 1 and kernels is None and torch.device(device).type == "cuda") else "nccl"
         self.exchange = exchange
         self._ipc_own, self._ipc_peers, self.peers = [], [], [(), ()]
-        if exchange == "p2p":
-            self._init_p2p(torch.device(device))
-        else:
+        if exchange == "p2p" and not self._init_p2p(torch.device(device), required=not auto):
+            self.exchange = exchange = "nccl"   # auto: CUDA IPC is not available between these processes
+        if exchange != "p2p":
             self.F = [torch.zeros(self.n[s], self.kp, dtype=torch.float64, device=device) for s in (0, 1)]
         self.ranges, self.shard = [], []
         for side, (rp, col, val) in enumerate((csr_user, csr_item)):
@@ -149,26 +150,53 @@ class ShardedWals:
         self.launches = 0
         self.timing = None  # optional dict of torch.cuda.Event pairs filled by half_step(record=True)
 
-    def _init_p2p(self, device):
-        """Factor replicas as CUDA-IPC allocations; every rank maps every other rank's replicas."""
+    def _init_p2p(self, device, required=True):
+        """Factor replicas as CUDA-IPC allocations; every rank maps every other rank's replicas.
+        Returns False (after releasing everything, on EVERY rank) if some rank could not export or map
+        a replica and `required` is False - e.g. processes in different IPC namespaces."""
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        self.F, handles = [], []
-        for s in (0, 1):
-            ptr, handle = self.kern.ipc_alloc(idx, self.n[s] * self.kp * 8)
-            self._ipc_own.append(ptr)
-            handles.append(handle)
-            self.F.append(torch.as_tensor(_DeviceBuffer(ptr, (self.n[s], self.kp)), device=device))
+        self.F, handles, err = [], [], None
+        try:
+            import os
+            if os.environ.get("QMFB_FORCE_NO_IPC"):  # test hook for the fallback below
+                raise RuntimeError("CUDA IPC disabled by QMFB_FORCE_NO_IPC")
+            for s in (0, 1):
+                ptr, handle = self.kern.ipc_alloc(idx, self.n[s] * self.kp * 8)
+                self._ipc_own.append(ptr)
+                handles.append(handle)
+        except Exception as e:  # noqa: BLE001 - reported below, collectively
+            err, handles = e, None
         gathered = [None] * self.world
         dist.all_gather_object(gathered, handles)
         peers = [[], []]
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            for s in (0, 1):
-                p = self.kern.ipc_open(idx, gathered[r][s])
-                self._ipc_peers.append(p)
-                peers[s].append(p)
+        if err is None and all(g is not None for g in gathered):
+            try:
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    for s in (0, 1):
+                        p = self.kern.ipc_open(idx, gathered[r][s])
+                        self._ipc_peers.append(p)
+                        peers[s].append(p)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("another rank could not allocate its shareable replicas")
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            for p in self._ipc_peers:
+                self.kern.ipc_close(p)
+            dist.barrier()   # nobody frees a replica another rank still has mapped
+            for p in self._ipc_own:
+                self.kern.ipc_free(p)
+            self._ipc_own, self._ipc_peers, self.F = [], [], []
+            if required:
+                raise RuntimeError("p2p exchange unavailable: %s" % (err if err is not None else "failed on another rank"))
+            return False
+        self.F = [torch.as_tensor(_DeviceBuffer(self._ipc_own[s], (self.n[s], self.kp)), device=device) for s in (0, 1)]
         self.peers = [tuple(peers[0]), tuple(peers[1])]
+        return True
 
     def close(self):
         """Unmap the peers' replicas and free our own (p2p exchange); collective: call on every rank."""
