@@ -52,6 +52,19 @@ int64_t qmfb_gram_workspace_len(int k);   /* doubles of scratch qmfb_gram_dev ne
  * results of several ranks are combined by summing gram_packed element-wise (NCCL allreduce). */
 int qmfb_gram_dev(void* stream, const double* Y, int64_t ldy, int64_t row_begin, int64_t row_end, int k,
                   double* workspace, double* gram_packed);
+/* The same Gram as a sum over a FIXED set of row parts, so that several devices can share the work and
+ * still produce bit-identical results: the rows [row_begin, row_end) are cut into
+ * P = qmfb_gram_parts_count(row_end - row_begin, k) parts that depend only on the row count;
+ * qmfb_gram_parts_dev writes the partial Gram of parts [part_begin, part_end) into
+ * workspace[part * qmfb_gram_packed_len(k) ...]; qmfb_gram_reduce_parts_dev sums all P parts in part
+ * order, part p being read from workspaces[d] for part_end[d-1] <= p < part_end[d] (host arrays of
+ * `nsrc` <= 16 entries; the pointers may be peer memory of other GPUs).  qmfb_gram_dev is the
+ * nsrc == 1 case.  Y must be 16-byte aligned, ldy even; the pad columns [k, ldy) of Y must be zero. */
+int qmfb_gram_parts_count(int64_t nrows, int k);
+int qmfb_gram_parts_dev(void* stream, const double* Y, int64_t ldy, int64_t row_begin, int64_t row_end, int k, int part_begin,
+                        int part_end, double* workspace);
+int qmfb_gram_reduce_parts_dev(void* stream, const double* const* workspaces, const int* part_end, int nsrc, int k,
+                               double* gram_packed);
 /* packed upper tiles -> dense symmetric k x k row-major */
 int qmfb_gram_unpack_dev(void* stream, const double* gram_packed, int k, double* out);
 /* Solve `nrows` rows of one half-step (replaces the per-row body of WALSEngine::iterate,
@@ -117,6 +130,41 @@ int64_t qmfb_wals_launch_count(qmfb_wals_t* h);
 /* device milliseconds (CUDA events on the handle's stream) spent in the last half-step's Gram
  * and row-solve kernels */
 int qmfb_wals_last_timing(qmfb_wals_t* h, float* gram_ms, float* solve_ms);
+
+/* ---------------------------------------------------------------- WALS across the GPUs of one box --
+ * One process, one handle, `ndev` GPUs (dev_ids; a device may be listed more than once - its shards then
+ * share that GPU).  Users and items are each cut into ndev contiguous row ranges balanced by nnz; every
+ * device keeps full replicas of both factor matrices.  A half-step is: partial Gram parts on every
+ * device -> each device sums all parts over NVLink peer memory -> solve of the device's rows with the
+ * all-gather fused into the solve kernel as peer stores -> row losses summed on the first device.  No
+ * library collective; results (factors AND loss) are bit-identical for every ndev, including
+ * qmfb_wals_* on one GPU.  This is what `wals --ngpus N` binds (WALSEngine::iterate,
+ * qmf/wals/WALSEngine.cpp:165-218; the reference's own multi-worker mode is distributed/, out of scope). */
+typedef struct qmfb_wals_sharded qmfb_wals_sharded_t;
+typedef struct qmfb_signals qmfb_signals_t;   /* GPU-built ingest handle, see "dataset ingest" below */
+int qmfb_wals_sharded_create(int ndev, const int* dev_ids, int64_t nusers, int64_t nitems, int nfactors,
+                             qmfb_wals_sharded_t** out);
+int qmfb_wals_sharded_destroy(qmfb_wals_sharded_t* h);
+int qmfb_wals_sharded_ndev(const qmfb_wals_sharded_t* h);
+/* FULL CSR of one orientation on the host (row_ptr has n[side]+1 entries); the library cuts and uploads */
+int qmfb_wals_sharded_set_csr(qmfb_wals_sharded_t* h, int side, const int64_t* row_ptr, const int32_t* col_idx, const double* val);
+/* both orientations from a GPU-built ingest handle, device to device (peer copies of each shard) */
+int qmfb_wals_sharded_set_signals(qmfb_wals_sharded_t* h, const qmfb_signals_t* s);
+/* device / row range / nnz of shard `slot` for one side (after set_csr / set_signals) */
+int qmfb_wals_sharded_shard(const qmfb_wals_sharded_t* h, int slot, int side, int* device, int64_t* row_begin, int64_t* nrows,
+                            int64_t* nnz);
+/* host n x nfactors row-major -> every replica;  replica of shard `slot` -> host */
+int qmfb_wals_sharded_set_factors(qmfb_wals_sharded_t* h, int side, const double* host);
+int qmfb_wals_sharded_get_factors(qmfb_wals_sharded_t* h, int side, int slot, double* host);
+/* as qmfb_wals_half_step / qmfb_wals_epoch_host; in epoch_host every device moves the rows it solved
+ * over its own PCIe link (pinned host buffers keep the copies asynchronous) */
+int qmfb_wals_sharded_half_step(qmfb_wals_sharded_t* h, int update_side, double alpha, double lambda, double* loss_sum);
+int qmfb_wals_sharded_epoch_host(qmfb_wals_sharded_t* h, double alpha, double lambda, const double* item_factors_in,
+                                 double* user_factors_out, double* item_factors_out, double* loss_out);
+double* qmfb_wals_sharded_factors_device(qmfb_wals_sharded_t* h, int side, int slot);
+int64_t qmfb_wals_sharded_launch_count(qmfb_wals_sharded_t* h);
+/* device ms of the last half-step's Gram (parts + reduce) and solve on the first device */
+int qmfb_wals_sharded_last_timing(qmfb_wals_sharded_t* h, float* gram_ms, float* solve_ms);
 
 /* ---------------------------------------------------------------- BPR engine (host) -------- */
 typedef struct qmfb_bpr qmfb_bpr_t;
@@ -185,10 +233,10 @@ int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double*
  * dense indices (idx = rank of the id among the distinct ids, the reference's assignment) and both
  * CSR orientations (rows by row id, cells by column id, duplicates kept in file order) plus the
  * longest-first row order the solve kernel deals rows in.  Inputs are host arrays. */
-typedef struct qmfb_signals qmfb_signals_t;
 int qmfb_signals_build(int device, int64_t nnz, const int64_t* user_ids, const int64_t* item_ids, const double* values,
                        qmfb_signals_t** out);
 int qmfb_signals_destroy(qmfb_signals_t* s);
+int qmfb_signals_device_ordinal(const qmfb_signals_t* s);   /* the CUDA device the handle lives on */
 int qmfb_signals_dims(const qmfb_signals_t* s, int64_t* nusers, int64_t* nitems, int64_t* nnz);
 /* ids_host[idx] = raw id of dense index idx (n[side] entries, ascending) */
 int qmfb_signals_ids(const qmfb_signals_t* s, int side, int64_t* ids_host);

@@ -119,6 +119,8 @@ def ref():
                                         c_f64]),
         "ref_wals_update_rows": (c_f64, [p_f64, c_i64, p_f64, c_i64, c_i64, p_i64, p_i32, p_f64, p_f64, c_f64, c_f64,
                                          C.c_int, C.POINTER(c_f64)]),
+        "ref_wals_update_rows_losses": (c_f64, [p_f64, c_i64, p_f64, c_i64, c_i64, p_i64, p_i32, p_f64, p_f64, c_f64,
+                                                c_f64, C.c_int, p_f64]),
         "ref_linear_symmetric_solve": (None, [p_f64, p_f64, c_i64, p_f64]),
         "ref_bpr_create": (vp, [c_i64, c_i64, c_f64, c_f64, c_f64, c_f64, c_f64, C.c_int, c_f64, c_i64, c_i64, C.c_int,
                                 c_i64, C.c_int32, C.c_int, C.c_char_p, c_i64, C.c_int, c_i64]),

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE — NOT PART OF THE PRODUCT.
 //
 // C-ABI harness around the UNMODIFIED reference sources in /root/reference (compiled where they
-// lie by oracle/build_ref.sh into oracle/_ref/libqmf_ref.so).  It exposes the reference's own
+// lie by oracle/Makefile into oracle/_ref/libqmf_ref.so).  It exposes the reference's own
 // implementation of every function on the hot path so that tests/ and
 // bench.py's cpu_baseline / --impl reference leg can (a) validate the C restatement in
 // oracle/qmf_oracle.c and (b) time the reference on the GPU box's host cores.
@@ -95,6 +95,28 @@ class WALSEngine_init_Test {
     }
     auto map = [&](const size_t t) {
       return WALSEngine::updateFactorsForOne(X, leftIndex, Y, rightIndex, groups[t], YtY, alpha, lambda);
+    };
+    auto reduce = [](double a, double b) { return a + b; };
+    return e.parallel_.mapReduce(static_cast<size_t>(nrows), map, reduce, 0.0);
+  }
+  // same, and the loss term of every row is kept (rowLoss[t]); for the sampled-row parity checks at
+  // the BASELINE-sized configs
+  static double updateRowsLosses(WALSEngine& e, Matrix& X, const Matrix& Y, const int64_t* rowPtr, const int32_t* cols,
+                                 const double* vals, int64_t nrows, const Matrix& YtY, double alpha, double lambda,
+                                 double* rowLoss) {
+    IdIndex leftIndex, rightIndex;
+    for (size_t i = 0; i < X.nrows(); ++i) leftIndex.getOrSetIdx(static_cast<int64_t>(i));
+    for (size_t i = 0; i < Y.nrows(); ++i) rightIndex.getOrSetIdx(static_cast<int64_t>(i));
+    std::vector<WALSEngine::SignalGroup> groups(nrows);
+    for (int64_t r = 0; r < nrows; ++r) {
+      groups[r].sourceId = r;
+      for (int64_t s = rowPtr[r]; s < rowPtr[r + 1]; ++s) {
+        groups[r].group.push_back(WALSEngine::Signal{cols[s], vals[s]});
+      }
+    }
+    auto map = [&](const size_t t) {
+      rowLoss[t] = WALSEngine::updateFactorsForOne(X, leftIndex, Y, rightIndex, groups[t], YtY, alpha, lambda);
+      return rowLoss[t];
     };
     auto reduce = [](double a, double b) { return a + b; };
     return e.parallel_.mapReduce(static_cast<size_t>(nrows), map, reduce, 0.0);
@@ -304,6 +326,22 @@ double ref_wals_update_rows(double* X, int64_t nrows, const double* Y, int64_t n
   const double loss = WALSEngine_init_Test::updateRows(e, Xm, Ym, rowPtr, cols, vals, nrows, G, alpha, lambda);
   const auto t1 = std::chrono::steady_clock::now();
   if (seconds != nullptr) *seconds = std::chrono::duration<double>(t1 - t0).count();
+  dumpMatrix(Xm, X);
+  return loss;
+}
+
+// as ref_wals_update_rows, also returning every row's loss term in rowLoss[nrows]
+double ref_wals_update_rows_losses(double* X, int64_t nrows, const double* Y, int64_t nright, int64_t k,
+                                   const int64_t* rowPtr, const int32_t* cols, const double* vals, const double* YtY,
+                                   double alpha, double lambda, int nthreads, double* rowLoss) {
+  WALSConfig cfg{1, static_cast<size_t>(k), lambda, alpha, 0.01, ""};
+  std::unique_ptr<MetricsEngine> none;
+  WALSEngine e(cfg, none, static_cast<size_t>(nthreads));
+  Matrix Xm(static_cast<size_t>(nrows), static_cast<size_t>(k)), Ym(static_cast<size_t>(nright), static_cast<size_t>(k)),
+    G(static_cast<size_t>(k), static_cast<size_t>(k));
+  fillMatrix(Ym, Y);
+  fillMatrix(G, YtY);
+  const double loss = WALSEngine_init_Test::updateRowsLosses(e, Xm, Ym, rowPtr, cols, vals, nrows, G, alpha, lambda, rowLoss);
   dumpMatrix(Xm, X);
   return loss;
 }

@@ -43,6 +43,9 @@ _SIG = {
     "qmfb_gram_packed_len": (c_i64, [C.c_int]),
     "qmfb_gram_workspace_len": (c_i64, [C.c_int]),
     "qmfb_gram_dev": (C.c_int, [vp, vp, c_i64, c_i64, c_i64, C.c_int, vp, vp]),
+    "qmfb_gram_parts_count": (C.c_int, [c_i64, C.c_int]),
+    "qmfb_gram_parts_dev": (C.c_int, [vp, vp, c_i64, c_i64, c_i64, C.c_int, C.c_int, C.c_int, vp]),
+    "qmfb_gram_reduce_parts_dev": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int, vp]),
     "qmfb_gram_unpack_dev": (C.c_int, [vp, vp, C.c_int, vp]),
     "qmfb_wals_solve_dev": (C.c_int, [vp, vp, c_i64, c_i64, vp, c_i64, C.c_int, vp, vp, vp, vp, c_i64, vp, c_f64, c_f64,
                                       vp, vp, vp]),
@@ -64,6 +67,20 @@ _SIG = {
     "qmfb_wals_stream": (vp, [vp]),
     "qmfb_wals_launch_count": (c_i64, [vp]),
     "qmfb_wals_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "qmfb_wals_sharded_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), c_i64, c_i64, C.c_int, C.POINTER(vp)]),
+    "qmfb_wals_sharded_destroy": (C.c_int, [vp]),
+    "qmfb_wals_sharded_ndev": (C.c_int, [vp]),
+    "qmfb_wals_sharded_set_csr": (C.c_int, [vp, C.c_int, p_i64, p_i32, p_f64]),
+    "qmfb_wals_sharded_set_signals": (C.c_int, [vp, vp]),
+    "qmfb_wals_sharded_shard": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(c_i64), C.POINTER(c_i64),
+                                          C.POINTER(c_i64)]),
+    "qmfb_wals_sharded_set_factors": (C.c_int, [vp, C.c_int, p_f64]),
+    "qmfb_wals_sharded_get_factors": (C.c_int, [vp, C.c_int, C.c_int, p_f64]),
+    "qmfb_wals_sharded_half_step": (C.c_int, [vp, C.c_int, c_f64, c_f64, C.POINTER(c_f64)]),
+    "qmfb_wals_sharded_epoch_host": (C.c_int, [vp, c_f64, c_f64, vp, vp, vp, C.POINTER(c_f64)]),
+    "qmfb_wals_sharded_factors_device": (vp, [vp, C.c_int, C.c_int]),
+    "qmfb_wals_sharded_launch_count": (c_i64, [vp]),
+    "qmfb_wals_sharded_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "qmfb_bpr_create": (C.c_int, [C.c_int, c_i64, c_i64, C.c_int, C.c_int, C.POINTER(vp)]),
     "qmfb_bpr_destroy": (C.c_int, [vp]),
     "qmfb_bpr_set_data": (C.c_int, [vp, p_i32, p_i32, c_i64]),
@@ -86,6 +103,7 @@ _SIG = {
                                      vp]),
     "qmfb_signals_build": (C.c_int, [C.c_int, c_i64, p_i64, p_i64, p_f64, C.POINTER(vp)]),
     "qmfb_signals_destroy": (C.c_int, [vp]),
+    "qmfb_signals_device_ordinal": (C.c_int, [vp]),
     "qmfb_signals_dims": (C.c_int, [vp, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "qmfb_signals_ids": (C.c_int, [vp, C.c_int, p_i64]),
     "qmfb_signals_csr": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),

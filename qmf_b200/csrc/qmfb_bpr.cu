@@ -373,12 +373,9 @@ int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double*
     return set_error(QMFB_ERR_INVALID, "qmfb_eval_rank_dev: bad argument");
   }
   auto st = static_cast<cudaStream_t>(stream);
-  static bool configured = false;
   const size_t smem = eval_smem_bytes(k);
-  if (!configured) {
-    QMFB_CUDA(cudaFuncSetAttribute(eval_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  // per device / context attribute: set on every call (cheap), a process may use several devices
+  QMFB_CUDA(cudaFuncSetAttribute(eval_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (smem > 200 * 1024) return set_error(QMFB_ERR_UNSUPPORTED, "nfactors too large for the evaluation kernel");
   QMFB_CUDA(cudaMemsetAsync(error, 0, sizeof(int32_t), st));
   QMFB_CUDA(cudaMemsetAsync(cnt, 0, size_t(nlabels + nT) * sizeof(int32_t), st));

@@ -38,9 +38,14 @@ int qmfb_ipc_alloc(int device, int64_t bytes, void** ptr, void* handle64) {
   if (bytes < 1 || !ptr || !handle64) return qmfb::set_error(QMFB_ERR_INVALID, "qmfb_ipc_alloc: bad argument");
   QMFB_CUDA(cudaSetDevice(device));
   QMFB_CUDA(cudaMalloc(ptr, size_t(bytes)));
-  QMFB_CUDA(cudaMemset(*ptr, 0, size_t(bytes)));
   cudaIpcMemHandle_t h;
-  QMFB_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  cudaError_t e = cudaMemset(*ptr, 0, size_t(bytes));
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return qmfb::set_error(QMFB_ERR_CUDA, "qmfb_ipc_alloc: %s", cudaGetErrorString(e));
+  }
   memcpy(handle64, &h, sizeof h);
   return QMFB_OK;
 }

@@ -21,4 +21,13 @@ int set_error(int code, const char* fmt, ...);
     }                                                                                                         \
   } while (0)
 
+// ---- helpers shared between translation units (qmfb_ingest.cu) ----
+// out[r] = row_ptr[row_begin + r] - row_ptr[row_begin], r = 0 .. nrows (device arrays, asynchronous on st)
+int rebase_row_ptr(cudaStream_t st, const int64_t* row_ptr, int64_t row_begin, int64_t nrows, int64_t* out);
+// order = local rows longest first (stable), the order the persistent solve kernel deals rows in;
+// device arrays, current device, synchronous
+int longest_first_order(const int64_t* row_ptr_local, int64_t nrows, int64_t nnz, int32_t* order);
+// out[0] = sum of v[0..n) in a fixed order (single block, fixed strides + fixed tree), asynchronous (qmfb_wals.cu)
+int det_sum_launch(cudaStream_t st, const double* v, int64_t n, double* out);
+
 }  // namespace qmfb

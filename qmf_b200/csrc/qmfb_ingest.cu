@@ -160,6 +160,41 @@ int build_side(qmfb_signals* s, int side, const int32_t* d_ridx, const int32_t* 
 
 }  // namespace
 
+namespace qmfb {
+
+__global__ void rebase_row_ptr_kernel(const int64_t* __restrict__ row_ptr, int64_t row_begin, int64_t nrows, int64_t* __restrict__ out) {
+  const int64_t base = row_ptr[row_begin];
+  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r <= nrows; r += int64_t(gridDim.x) * blockDim.x) {
+    out[r] = row_ptr[row_begin + r] - base;
+  }
+}
+
+int rebase_row_ptr(cudaStream_t st, const int64_t* row_ptr, int64_t row_begin, int64_t nrows, int64_t* out) {
+  rebase_row_ptr_kernel<<<grid_for(nrows + 1), 256, 0, st>>>(row_ptr, row_begin, nrows, out);
+  QMFB_CUDA(cudaGetLastError());
+  return QMFB_OK;
+}
+
+int longest_first_order(const int64_t* row_ptr_local, int64_t nrows, int64_t nnz, int32_t* order) {
+  if (nrows < 1) return QMFB_OK;
+  DevBuf len_in, len_out, iota, tmp;
+  if (int rc = dev_alloc(len_in, size_t(nrows) * 8)) return rc;
+  if (int rc = dev_alloc(len_out, size_t(nrows) * 8)) return rc;
+  if (int rc = dev_alloc(iota, size_t(nrows) * 4)) return rc;
+  row_len_kernel<<<grid_for(nrows), 256>>>(row_ptr_local, nrows, len_in.as<uint64_t>(), iota.as<int32_t>());
+  QMFB_CUDA(cudaGetLastError());
+  size_t bytes = 0;
+  QMFB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, len_in.as<uint64_t>(), len_out.as<uint64_t>(), iota.as<int32_t>(), order,
+                                                      nrows, 0, bits_for(nnz + 1)));
+  if (int rc = dev_alloc(tmp, bytes)) return rc;
+  QMFB_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, len_in.as<uint64_t>(), len_out.as<uint64_t>(), iota.as<int32_t>(), order,
+                                                      nrows, 0, bits_for(nnz + 1)));
+  QMFB_CUDA(cudaDeviceSynchronize());
+  return QMFB_OK;
+}
+
+}  // namespace qmfb
+
 extern "C" {
 
 int qmfb_signals_destroy(qmfb_signals_t* s) {
@@ -214,6 +249,8 @@ int qmfb_signals_build(int device, int64_t nnz, const int64_t* user_ids, const i
   *out = s;
   return QMFB_OK;
 }
+
+int qmfb_signals_device_ordinal(const qmfb_signals_t* s) { return s ? s->device : -1; }
 
 int qmfb_signals_dims(const qmfb_signals_t* s, int64_t* nusers, int64_t* nitems, int64_t* nnz) {
   if (!s) return set_error(QMFB_ERR_INVALID, "qmfb_signals_dims: null handle");

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <numeric>
 #include <vector>
 
@@ -12,23 +13,50 @@ namespace qmfb {
 
 constexpr int kGramMaxParts = 296;  // 2 CTAs per SM on a 148-SM B200
 
-template <int NT>
-static int launch_gram(cudaStream_t st, const double* Y, int64_t ldy, int64_t r0, int64_t r1, int k, double* ws,
-                       double* packed) {
-  using SM = WalsSmem<NT>;
-  static bool configured = false;
-  if (!configured) {
-    QMFB_CUDA(cudaFuncSetAttribute(gram_partial_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
-    configured = true;
+// Per-DEVICE launch configuration.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the
+// current device/context only and the occupancy-derived grid cap depends on the device, so the state
+// is kept per device ordinal (a process may drive several GPUs: qmfb_wals_sharded_*, --ngpus) and is
+// guarded for concurrent host threads.
+constexpr int kMaxDevices = 64;
+struct PerDeviceCfg {
+  std::mutex mu;
+  bool done[kMaxDevices] = {};
+  int value[kMaxDevices] = {};
+};
+// runs init(dev, value) once per device; returns the cached value through *out
+template <class Init>
+static int per_device(PerDeviceCfg& cfg, int* out, Init&& init) {
+  int dev = 0;
+  QMFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return set_error(QMFB_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  if (!cfg.done[dev]) {
+    int v = 0;
+    if (int rc = init(dev, &v)) return rc;
+    cfg.value[dev] = v;
+    cfg.done[dev] = true;
   }
-  const int64_t n = r1 - r0;
-  int parts = int(std::min<int64_t>(kGramMaxParts, std::max<int64_t>(1, (n + 4 * kChunk - 1) / (4 * kChunk))));
-  gram_partial_kernel<NT><<<parts, SM::NTHREADS, SM::kBytes, st>>>(Y, ldy, r0, r1, ws);
+  if (out) *out = cfg.value[dev];
+  return QMFB_OK;
+}
+
+// Number of fixed row parts the Gram of an n-row matrix is summed over (one CTA per part)
+static int gram_nparts(int64_t n, int kp) {
+  if (kp <= 128) return int(std::min<int64_t>(kGramMaxParts, std::max<int64_t>(1, (n + 4 * kChunk - 1) / (4 * kChunk))));
+  return int(std::min<int64_t>(kGramMaxParts / 2, std::max<int64_t>(1, (n + 4 * kBigRows - 1) / (4 * kBigRows))));
+}
+
+template <int NT>
+static int launch_gram_parts(cudaStream_t st, const double* Y, int64_t ldy, int64_t r0, int64_t r1, int p0, int p1, double* ws) {
+  using SM = WalsSmem<NT>;
+  static PerDeviceCfg cfg;
+  if (int rc = per_device(cfg, nullptr, [](int, int*) -> int {
+        QMFB_CUDA(cudaFuncSetAttribute(gram_partial_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+        return QMFB_OK;
+      })) return rc;
+  if (p1 <= p0) return QMFB_OK;
+  gram_partial_kernel<NT><<<p1 - p0, SM::NTHREADS, SM::kBytes, st>>>(Y, ldy, r0, r1, ws, p0, gram_nparts(r1 - r0, SM::KP));
   QMFB_CUDA(cudaGetLastError());
-  const int nelem = SM::NTILE_A * 64;
-  gram_reduce_kernel<<<(nelem + 255) / 256, 256, 0, st>>>(ws, parts, nelem, packed);
-  QMFB_CUDA(cudaGetLastError());
-  (void)k;
   return QMFB_OK;
 }
 
@@ -36,43 +64,37 @@ static int launch_gram(cudaStream_t st, const double* Y, int64_t ldy, int64_t r0
 // default gives freed memory back to the driver at the next synchronisation: every call would then pay
 // a real allocation.  Keep the pool's memory cached (once per device).
 static int keep_pool_cached() {
-  static bool done[64] = {false};
-  int dev = 0;
-  QMFB_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !done[dev]) {
+  static PerDeviceCfg cfg;
+  return per_device(cfg, nullptr, [](int dev, int*) -> int {
     cudaMemPool_t pool;
     QMFB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t keep = UINT64_MAX;
     QMFB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    done[dev] = true;
-  }
-  return QMFB_OK;
+    return QMFB_OK;
+  });
 }
 
 template <int NT>
 static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_sum, int32_t* scratch) {
   if (int rc = keep_pool_cached()) return rc;
   using SM = WalsSmem<NT>;
-  static int grid_cap = 0;
-  if (grid_cap == 0) {
-    QMFB_CUDA(cudaFuncSetAttribute(wals_solve_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
-    int dev = 0, sms = 0, occ = 0;
-    QMFB_CUDA(cudaGetDevice(&dev));
-    QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    QMFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wals_solve_kernel<NT>, SM::NTHREADS, SM::kBytes));
-    if (occ < 1) return set_error(QMFB_ERR_CUDA, "wals_solve_kernel does not fit on an SM");
-    grid_cap = sms * occ;
-  }
+  static PerDeviceCfg cfg;
+  int grid_cap = 0;
+  if (int rc = per_device(cfg, &grid_cap, [](int dev, int* cap) -> int {
+        QMFB_CUDA(cudaFuncSetAttribute(wals_solve_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+        QMFB_CUDA(cudaFuncSetAttribute(long_row_partial_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+        int sms = 0, occ = 0;
+        QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        QMFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wals_solve_kernel<NT>, SM::NTHREADS, SM::kBytes));
+        if (occ < 1) return set_error(QMFB_ERR_CUDA, "wals_solve_kernel does not fit on an SM");
+        *cap = sms * occ;
+        return QMFB_OK;
+      })) return rc;
   QMFB_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(int32_t), st));
   if (prm.nrows > 0) {
     const int grid = int(std::min<int64_t>(grid_cap, prm.nrows));
     // extremely long rows at the head of `order` are summed by many CTAs ahead of the solve kernel
     // (two empty launches when there is none); stream-ordered scratch, freed after the kernel
-    static bool long_configured = false;
-    if (!long_configured) {
-      QMFB_CUDA(cudaFuncSetAttribute(long_row_partial_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
-      long_configured = true;
-    }
     constexpr int kLen = LongRow<NT>::kLen;
     double* long_buf = nullptr;
     QMFB_CUDA(cudaMallocAsync(&long_buf, size_t(kLongMax) * (kLongParts + 1) * kLen * sizeof(double), st));
@@ -95,19 +117,15 @@ static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_su
 
 // ---- 128 < k <= 256: tiles in an L2-resident global workspace (wals_big.cuh) ----------------
 template <int NT>
-static int launch_gram_big(cudaStream_t st, const double* Y, int64_t ldy, int64_t r0, int64_t r1, double* ws, double* packed) {
+static int launch_gram_parts_big(cudaStream_t st, const double* Y, int64_t ldy, int64_t r0, int64_t r1, int p0, int p1, double* ws) {
   using SM = WalsSmemBig<NT>;
-  static bool configured = false;
-  if (!configured) {
-    QMFB_CUDA(cudaFuncSetAttribute(gram_partial_big_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
-    configured = true;
-  }
-  const int64_t n = r1 - r0;
-  const int parts = int(std::min<int64_t>(kGramMaxParts / 2, std::max<int64_t>(1, (n + 4 * kBigRows - 1) / (4 * kBigRows))));
-  gram_partial_big_kernel<NT><<<parts, SM::NTHREADS, SM::kBytes, st>>>(Y, ldy, r0, r1, ws);
-  QMFB_CUDA(cudaGetLastError());
-  const int nelem = SM::NTILE_A * 64;
-  gram_reduce_kernel<<<(nelem + 255) / 256, 256, 0, st>>>(ws, parts, nelem, packed);
+  static PerDeviceCfg cfg;
+  if (int rc = per_device(cfg, nullptr, [](int, int*) -> int {
+        QMFB_CUDA(cudaFuncSetAttribute(gram_partial_big_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+        return QMFB_OK;
+      })) return rc;
+  if (p1 <= p0) return QMFB_OK;
+  gram_partial_big_kernel<NT><<<p1 - p0, SM::NTHREADS, SM::kBytes, st>>>(Y, ldy, r0, r1, ws, p0, gram_nparts(r1 - r0, SM::KP));
   QMFB_CUDA(cudaGetLastError());
   return QMFB_OK;
 }
@@ -115,13 +133,13 @@ static int launch_gram_big(cudaStream_t st, const double* Y, int64_t ldy, int64_
 template <int NT>
 static int launch_solve_big(cudaStream_t st, const SolveParams& prm, double* loss_sum, int32_t* scratch) {
   using SM = WalsSmemBig<NT>;
-  static int sms = 0;
-  if (sms == 0) {
-    QMFB_CUDA(cudaFuncSetAttribute(wals_solve_big_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
-    int dev = 0;
-    QMFB_CUDA(cudaGetDevice(&dev));
-    QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static PerDeviceCfg cfg;
+  int sms = 0;
+  if (int rc = per_device(cfg, &sms, [](int dev, int* out) -> int {
+        QMFB_CUDA(cudaFuncSetAttribute(wals_solve_big_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::kBytes)));
+        QMFB_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+        return QMFB_OK;
+      })) return rc;
   if (int rc = keep_pool_cached()) return rc;
   QMFB_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(int32_t), st));
   if (prm.nrows > 0) {
@@ -134,6 +152,12 @@ static int launch_solve_big(cudaStream_t st, const SolveParams& prm, double* los
     QMFB_CUDA(e);
   }
   sum_kernel<<<1, 1024, 0, st>>>(prm.row_loss, prm.nrows, loss_sum);
+  QMFB_CUDA(cudaGetLastError());
+  return QMFB_OK;
+}
+
+int det_sum_launch(cudaStream_t st, const double* v, int64_t n, double* out) {
+  sum_kernel<<<1, 1024, 0, st>>>(v, n, out);
   QMFB_CUDA(cudaGetLastError());
   return QMFB_OK;
 }
@@ -178,23 +202,64 @@ int64_t qmfb_gram_workspace_len(int k) {
   return n < 0 ? n : n * kGramMaxParts;
 }
 
+int qmfb_gram_parts_count(int64_t nrows, int k) {
+  const int kp = qmfb_padded_k(k);
+  if (kp < 0) return kp;
+  if (nrows < 0) return set_error(QMFB_ERR_INVALID, "qmfb_gram_parts_count: bad argument");
+  return gram_nparts(nrows, kp);
+}
+
+int qmfb_gram_parts_dev(void* stream, const double* Y, int64_t ldy, int64_t row_begin, int64_t row_end, int k, int part_begin,
+                        int part_end, double* workspace) {
+  const int kp = qmfb_padded_k(k);
+  if (kp < 0) return kp;
+  if (ldy < kp || (ldy & 1) || (reinterpret_cast<uintptr_t>(Y) & 15) || row_end < row_begin || !Y || !workspace || part_begin < 0 ||
+      part_end < part_begin || part_end > gram_nparts(row_end - row_begin, kp)) {
+    return set_error(QMFB_ERR_INVALID, "qmfb_gram_parts_dev: bad argument (Y must be 16-byte aligned, ldy even and >= padded k)");
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (kp / 8) {
+    case 4: return launch_gram_parts<4>(st, Y, ldy, row_begin, row_end, part_begin, part_end, workspace);
+    case 8: return launch_gram_parts<8>(st, Y, ldy, row_begin, row_end, part_begin, part_end, workspace);
+    case 12: return launch_gram_parts<12>(st, Y, ldy, row_begin, row_end, part_begin, part_end, workspace);
+    case 16: return launch_gram_parts<16>(st, Y, ldy, row_begin, row_end, part_begin, part_end, workspace);
+    case 20: return launch_gram_parts_big<20>(st, Y, ldy, row_begin, row_end, part_begin, part_end, workspace);
+    case 24: return launch_gram_parts_big<24>(st, Y, ldy, row_begin, row_end, part_begin, part_end, workspace);
+    case 28: return launch_gram_parts_big<28>(st, Y, ldy, row_begin, row_end, part_begin, part_end, workspace);
+    case 32: return launch_gram_parts_big<32>(st, Y, ldy, row_begin, row_end, part_begin, part_end, workspace);
+  }
+  return set_error(QMFB_ERR_UNSUPPORTED, "unsupported padded k %d", kp);
+}
+
+int qmfb_gram_reduce_parts_dev(void* stream, const double* const* workspaces, const int* part_end, int nsrc, int k,
+                               double* gram_packed) {
+  const int64_t nelem = qmfb_gram_packed_len(k);
+  if (nelem < 0) return int(nelem);
+  if (!workspaces || !part_end || nsrc < 1 || nsrc > kMaxGramSrc || !gram_packed) {
+    return set_error(QMFB_ERR_INVALID, "qmfb_gram_reduce_parts_dev: bad argument");
+  }
+  GramReduceParams prm{};
+  for (int d = 0; d < nsrc; ++d) {
+    if (!workspaces[d] || part_end[d] < (d ? part_end[d - 1] : 0)) return set_error(QMFB_ERR_INVALID, "qmfb_gram_reduce_parts_dev: bad source %d", d);
+    prm.src[d] = workspaces[d];
+    prm.part_end[d] = part_end[d];
+  }
+  prm.nsrc = nsrc;
+  prm.nelem = int(nelem);
+  gram_reduce_kernel<<<(prm.nelem + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(prm, gram_packed);
+  QMFB_CUDA(cudaGetLastError());
+  return QMFB_OK;
+}
+
 int qmfb_gram_dev(void* stream, const double* Y, int64_t ldy, int64_t row_begin, int64_t row_end, int k,
                   double* workspace, double* gram_packed) {
   const int kp = qmfb_padded_k(k);
   if (kp < 0) return kp;
-  if (ldy < kp || row_end < row_begin || !Y || !workspace || !gram_packed) return set_error(QMFB_ERR_INVALID, "qmfb_gram_dev: bad argument");
-  auto st = static_cast<cudaStream_t>(stream);
-  switch (kp / 8) {
-    case 4: return launch_gram<4>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
-    case 8: return launch_gram<8>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
-    case 12: return launch_gram<12>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
-    case 16: return launch_gram<16>(st, Y, ldy, row_begin, row_end, k, workspace, gram_packed);
-    case 20: return launch_gram_big<20>(st, Y, ldy, row_begin, row_end, workspace, gram_packed);
-    case 24: return launch_gram_big<24>(st, Y, ldy, row_begin, row_end, workspace, gram_packed);
-    case 28: return launch_gram_big<28>(st, Y, ldy, row_begin, row_end, workspace, gram_packed);
-    case 32: return launch_gram_big<32>(st, Y, ldy, row_begin, row_end, workspace, gram_packed);
-  }
-  return set_error(QMFB_ERR_UNSUPPORTED, "unsupported padded k %d", kp);
+  if (row_end < row_begin || !gram_packed) return set_error(QMFB_ERR_INVALID, "qmfb_gram_dev: bad argument");
+  const int parts = gram_nparts(row_end - row_begin, kp);
+  if (int rc = qmfb_gram_parts_dev(stream, Y, ldy, row_begin, row_end, k, 0, parts, workspace)) return rc;
+  const double* src[1] = {workspace};
+  return qmfb_gram_reduce_parts_dev(stream, src, &parts, 1, k, gram_packed);
 }
 
 int qmfb_gram_unpack_dev(void* stream, const double* gram_packed, int k, double* out) {
@@ -233,6 +298,10 @@ int qmfb_wals_solve_peers_dev(void* stream, double* X, int64_t ldx, int64_t row_
   if (ldx < kp || ldy < kp || nrows < 0 || nrows > INT32_MAX || !X || !Y || !row_ptr || !order || !gram_packed || !row_loss ||
       !loss_sum || !scratch || npeers < 0 || npeers > kMaxPeers || (npeers > 0 && !peer_X)) {
     return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_dev: bad argument");
+  }
+  // the gather uses 16-byte cp.async on Y + row * ldy
+  if ((ldy & 1) || (reinterpret_cast<uintptr_t>(Y) & 15)) {
+    return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_dev: Y must be 16-byte aligned with an even row stride");
   }
   SolveParams prm{X, ldx, row_offset, Y, ldy, k, row_ptr, col, val, order, int(nrows), gram_packed, alpha, lambda,
                   row_loss, scratch + 1, npeers, {}, nullptr};

@@ -98,7 +98,7 @@ __device__ __forceinline__ void big_accumulate(const double* sb, const double* w
 template <int NT>
 __global__ void __launch_bounds__(WalsSmemBig<NT>::NTHREADS, 1)
     gram_partial_big_kernel(const double* __restrict__ Y, int64_t ldy, int64_t row_begin, int64_t row_end,
-                            double* __restrict__ partial) {
+                            double* __restrict__ partial, int part0, int nparts) {
   using SM = WalsSmemBig<NT>;
   extern __shared__ __align__(128) unsigned char smem[];
   double* sb = reinterpret_cast<double*>(smem + SM::kOffStage);
@@ -106,9 +106,10 @@ __global__ void __launch_bounds__(WalsSmemBig<NT>::NTHREADS, 1)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   constexpr int PPR = SM::KP / 2;
   const int64_t n = row_end - row_begin;
-  const int64_t r0 = row_begin + n * blockIdx.x / gridDim.x;
-  const int64_t r1 = row_begin + n * (blockIdx.x + 1) / gridDim.x;
-  double* out = partial + size_t(blockIdx.x) * SM::NTILE_A * 64;
+  const int part = part0 + int(blockIdx.x);  // see gram_partial_kernel
+  const int64_t r0 = row_begin + n * part / nparts;
+  const int64_t r1 = row_begin + n * (part + 1) / nparts;
+  double* out = partial + size_t(part) * SM::NTILE_A * 64;
   if (r1 <= r0) {
     for (int i = tid; i < SM::NTILE_A * 64; i += SM::NTHREADS) out[i] = 0.0;
     return;

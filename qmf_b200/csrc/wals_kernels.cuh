@@ -228,7 +228,11 @@ __device__ __forceinline__ int tile_acc_off(int lane) { return (lane >> 2) * 8 +
 template <int NT>
 __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(const double* __restrict__ Y, int64_t ldy,
                                                                               int64_t row_begin, int64_t row_end,
-                                                                              double* __restrict__ partial) {
+                                                                              double* __restrict__ partial, int part0,
+                                                                              int nparts) {
+  // CTA b sums part (part0 + b) of the `nparts` fixed row parts of [row_begin, row_end) into
+  // partial[part0 + b]: the parts and the order inside a part depend only on the row range, so the
+  // reduced Gram is bit-identical however the parts are dealt to devices (qmfb_wals_sharded_*)
   using SM = WalsSmem<NT>;
   extern __shared__ __align__(128) unsigned char smem[];
   double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
@@ -245,8 +249,9 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(co
   }
   __syncthreads();
   const int64_t n = row_end - row_begin;
-  const int64_t r0 = row_begin + n * blockIdx.x / gridDim.x;
-  const int64_t r1 = row_begin + n * (blockIdx.x + 1) / gridDim.x;
+  const int part = part0 + int(blockIdx.x);
+  const int64_t r0 = row_begin + n * part / nparts;
+  const int64_t r1 = row_begin + n * (part + 1) / nparts;
   const int nch = int((r1 - r0 + kChunk - 1) / kChunk);
 
   auto issue = [&](int c) {  // warp 0 only
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(co
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
   }
-  double* out = partial + size_t(blockIdx.x) * SM::NTILE_A * 64;
+  double* out = partial + size_t(part) * SM::NTILE_A * 64;
 #pragma unroll
   for (int t = 0; t <= NT; ++t) {
     int I, J;
@@ -284,12 +289,25 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(co
   }
 }
 
-// out[t] = sum_b partial[b][t] in fixed order (deterministic), t over NTILE_A*64 packed entries
-__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, int nelem, double* __restrict__ out) {
+// out[t] = sum_p partial[p][t] over parts p = 0 .. nparts-1 in that order (deterministic), t over the
+// NTILE_A*64 packed entries.  Part p lives in the workspace of the device that computed it:
+// src[d] for part_end[d-1] <= p < part_end[d] (local or NVLink peer memory; one device: nsrc == 1).
+constexpr int kMaxGramSrc = 16;
+struct GramReduceParams {
+  const double* src[kMaxGramSrc];
+  int part_end[kMaxGramSrc];
+  int nsrc;
+  int nelem;
+};
+__global__ void gram_reduce_kernel(const GramReduceParams prm, double* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nelem) return;
+  if (t >= prm.nelem) return;
   double s = 0.0;
-  for (int b = 0; b < nparts; ++b) s += partial[size_t(b) * nelem + t];
+  int p = 0;
+  for (int d = 0; d < prm.nsrc; ++d) {
+    const double* src = prm.src[d];
+    for (; p < prm.part_end[d]; ++p) s += src[size_t(p) * prm.nelem + t];
+  }
   out[t] = s;
 }
 

@@ -137,3 +137,77 @@ class WalsEngineHandle:
         g, s = C.c_float(), C.c_float()
         check(lib.qmfb_wals_last_timing(self._h, C.byref(g), C.byref(s)))
         return g.value, s.value
+
+
+class ShardedWalsHandle:
+    """WALS across several GPUs of one box from ONE process (qmfb_wals_sharded_*: what `wals --ngpus N`
+    binds).  `devices` lists CUDA ordinals; a device may repeat (its shards then share that GPU).  Factors
+    and loss are bit-identical to WalsEngineHandle for every device count."""
+
+    def __init__(self, nusers, nitems, nfactors, devices):
+        self.nusers, self.nitems, self.k = int(nusers), int(nitems), int(nfactors)
+        self.devices = [int(d) for d in devices]
+        self._h = None
+        h = C.c_void_p()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        check(lib.qmfb_wals_sharded_create(len(self.devices), arr, self.nusers, self.nitems, self.k, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib.qmfb_wals_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _n(self, side):
+        return self.nusers if side == SIDE_USER else self.nitems
+
+    def set_csr(self, side, row_ptr, col_idx, val):
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        assert len(row_ptr) == self._n(side) + 1
+        if col_idx.size == 0:
+            col_idx, val = np.zeros(1, np.int32), np.zeros(1, np.float64)
+        check(lib.qmfb_wals_sharded_set_csr(self._h, side, row_ptr, col_idx, val))
+
+    def set_signals(self, signals):
+        check(lib.qmfb_wals_sharded_set_signals(self._h, signals._h))
+
+    def shard(self, slot, side):
+        dev, b, n, nnz = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.qmfb_wals_sharded_shard(self._h, slot, side, C.byref(dev), C.byref(b), C.byref(n), C.byref(nnz)))
+        return dev.value, b.value, n.value, nnz.value
+
+    def set_factors(self, side, F):
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        assert F.shape == (self._n(side), self.k)
+        check(lib.qmfb_wals_sharded_set_factors(self._h, side, F))
+
+    def get_factors(self, side, slot=0):
+        F = np.empty((self._n(side), self.k), dtype=np.float64)
+        check(lib.qmfb_wals_sharded_get_factors(self._h, side, slot, F))
+        return F
+
+    def half_step(self, side, alpha, lam):
+        loss = C.c_double()
+        check(lib.qmfb_wals_sharded_half_step(self._h, side, alpha, lam, C.byref(loss)))
+        return loss.value / self.nusers / self.nitems
+
+    def epoch_host(self, alpha, lam, item_in=None, user_out=None, item_out=None):
+        loss = C.c_double()
+        pin = item_in.ctypes.data_as(C.c_void_p) if item_in is not None else None
+        pu = user_out.ctypes.data_as(C.c_void_p) if user_out is not None else None
+        pi = item_out.ctypes.data_as(C.c_void_p) if item_out is not None else None
+        check(lib.qmfb_wals_sharded_epoch_host(self._h, alpha, lam, pin, pu, pi, C.byref(loss)))
+        return loss.value
+
+    def launch_count(self):
+        return int(lib.qmfb_wals_sharded_launch_count(self._h))
+
+    def last_timing(self):
+        g, s = C.c_float(), C.c_float()
+        check(lib.qmfb_wals_sharded_last_timing(self._h, C.byref(g), C.byref(s)))
+        return g.value, s.value

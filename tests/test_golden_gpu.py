@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from util import rel_err
+from util import rel_err, rel_err_rows
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -27,8 +27,8 @@ def test_wals_epochs_match_reference(name):
     for e in range(len(g["losses"])):
         lu = h.half_step(0, float(g["alpha"]), float(g["lam"]))
         li = h.half_step(1, float(g["alpha"]), float(g["lam"]))
-        assert rel_err(h.get_factors(0), g["X"][e]) < 1e-9
-        assert rel_err(h.get_factors(1), g["Y"][e]) < 1e-9
+        assert rel_err_rows(h.get_factors(0), g["X"][e]) < 1e-9
+        assert rel_err_rows(h.get_factors(1), g["Y"][e]) < 1e-9
         assert abs(lu - g["losses"][e, 0]) <= 1e-12 * abs(lu)
         assert abs(li - g["losses"][e, 1]) <= 1e-12 * abs(li)
 
@@ -41,8 +41,8 @@ def test_bpr_steps_match_reference():
     h = BprEngineHandle(P0.shape[0], Q0.shape[0], P0.shape[1], use_biases=True)
     h.set_factors(0, P0); h.set_factors(1, Q0); h.set_biases(b0)
     h.update_triplets(g["step_u"], g["step_i"], g["step_j"], lr, lu, li, lb)
-    assert rel_err(h.get_factors(0), g["step_P"]) < 1e-13
-    assert rel_err(h.get_factors(1), g["step_Q"]) < 1e-13
+    assert rel_err_rows(h.get_factors(0), g["step_P"]) < 1e-13
+    assert rel_err_rows(h.get_factors(1), g["step_Q"]) < 1e-13
     assert rel_err(h.get_biases(), g["step_b"]) < 1e-13
 
 

@@ -4,7 +4,7 @@ the objective."""
 import numpy as np
 import pytest
 
-from util import init_factors, rel_err, uniform_dataset
+from util import init_factors, rel_err, rel_err_rows, uniform_dataset
 
 pytestmark = pytest.mark.gpu
 
@@ -55,8 +55,8 @@ def test_epochs_match_oracle(oracle_lib, nu, ni, nnz, k, dup):
         lu_o = oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, ucsr[0], ucsr[1], ucsr[2], alpha, lam, NU, NI, 16)
         li_o = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, icsr[0], icsr[1], icsr[2], alpha, lam, NU, NI, 16)
         Xg, Yg = h.get_factors(0), h.get_factors(1)
-        assert rel_err(Xg, X) < FACTOR_TOL, (epoch, "user factors")
-        assert rel_err(Yg, Y) < FACTOR_TOL, (epoch, "item factors")
+        assert rel_err_rows(Xg, X) < FACTOR_TOL, (epoch, "user factors")
+        assert rel_err_rows(Yg, Y) < FACTOR_TOL, (epoch, "item factors")
         assert abs(lu - lu_o) <= LOSS_TOL * abs(lu_o), (epoch, lu, lu_o)
         assert abs(li - li_o) <= LOSS_TOL * abs(li_o), (epoch, li, li_o)
 
@@ -75,11 +75,11 @@ def test_rank_deficient_gram_backward_error(oracle_lib):
     h.half_step(0, alpha, lam)
     oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, ucsr[0], ucsr[1], ucsr[2], alpha, lam, NU, NI, 16)
     Xg = h.get_factors(0)
-    assert rel_err(Xg, X) < 1e-9
+    assert rel_err_rows(Xg, X) < 1e-9
     h.half_step(1, alpha, lam)
     oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, icsr[0], icsr[1], icsr[2], alpha, lam, NU, NI, 16)
     Yg = h.get_factors(1)
-    assert rel_err(Yg, Y) < 1e-6
+    assert rel_err_rows(Yg, Y) < 1e-6
     G = X.T @ X
     worst_g = worst_o = 0.0
     for r in range(NI):
@@ -109,7 +109,7 @@ def test_row_shapes_edge_cases(oracle_lib):
     loss = h.half_step(0, 40.0, 0.05)
     X = np.zeros((len(lens), k))
     loss_o = oracle_lib.qmfo_wals_half_step(X, len(lens), Y, ni, k, row_ptr, col, val, 40.0, 0.05, len(lens), ni, 4)
-    assert rel_err(h.get_factors(0), X) < FACTOR_TOL
+    assert rel_err_rows(h.get_factors(0), X) < FACTOR_TOL
     assert abs(loss - loss_o) <= LOSS_TOL * abs(loss_o)
     assert np.all(h.get_factors(0)[4] == 0.0)  # empty row: A = G + lambda I, b = 0
 
@@ -139,7 +139,7 @@ def test_epoch_host_roundtrip(oracle_lib):
     Y = Y0.copy()
     oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, 30, ucsr[0], ucsr[1], ucsr[2], 40.0, 0.05, NU, NI, 16)
     lo = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, 30, icsr[0], icsr[1], icsr[2], 40.0, 0.05, NU, NI, 16)
-    assert rel_err(Xo, X) < FACTOR_TOL and rel_err(Yo, Y) < FACTOR_TOL
+    assert rel_err_rows(Xo, X) < FACTOR_TOL and rel_err_rows(Yo, Y) < FACTOR_TOL
     assert abs(loss - lo) <= LOSS_TOL * abs(lo)
 
 
@@ -198,8 +198,8 @@ def test_sharded_driver_single_rank_matches_oracle(oracle_lib):
         sw.check_error()
         oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, urp, uci, uv, 40.0, 0.05, NU, NI, 16)
         lo = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, irp, ici, iv, 40.0, 0.05, NU, NI, 16)
-        assert rel_err(sw.get_factors(0).cpu().numpy(), X) < FACTOR_TOL
-        assert rel_err(sw.get_factors(1).cpu().numpy(), Y) < FACTOR_TOL
+        assert rel_err_rows(sw.get_factors(0).cpu().numpy(), X) < FACTOR_TOL
+        assert rel_err_rows(sw.get_factors(1).cpu().numpy(), Y) < FACTOR_TOL
         assert abs(loss - lo) <= LOSS_TOL * abs(lo)
 
 
@@ -271,5 +271,5 @@ def test_extremely_long_row_is_built_by_many_ctas(oracle_lib):
     li = h.half_step(1, 40.0, 0.05)
     lu_o = oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, urp, uci, uv, 40.0, 0.05, NU, NI, 16)
     li_o = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, irp, ici, iv, 40.0, 0.05, NU, NI, 16)
-    assert rel_err(h.get_factors(0), X) < FACTOR_TOL and rel_err(h.get_factors(1), Y) < FACTOR_TOL
+    assert rel_err_rows(h.get_factors(0), X) < FACTOR_TOL and rel_err_rows(h.get_factors(1), Y) < FACTOR_TOL
     assert abs(lu - lu_o) <= LOSS_TOL * abs(lu_o) and abs(li - li_o) <= LOSS_TOL * abs(li_o)
