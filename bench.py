@@ -28,7 +28,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALPHA, LAMBDA = 40.0, 0.05          # reference defaults (qmf/wals.cpp:28-29)
-FP64_PEAK_TFLOPS = 37.1             # measured: profiles/r01_fp64_peak.txt (DMMA.8x8x4 register loop)
+
+
+def fp64_peak_tflops():
+    """FP64 DMMA peak, builder-measured on this pool's B200 (tools/fp64_peak.cu -> profiles/fp64_peak.json);
+    MEASURED_PEAKS.json carries no FP64 entry."""
+    with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
+        return float(json.load(f)["dmma_tflops"])
+
 
 
 def algorithmic_flops(n_rows, nnz, k):
@@ -264,39 +271,52 @@ def run_bpr_reference(threads):
             "sample": "2 epochs of BPREngine::optimize on the C2 shape, num_hogwild_threads = nthreads = %d" % threads}
 
 
-def run_eval_ours(device=0):
-    """north_star part 3: all-item scoring + rank statistics (eval_rank_kernel) on the C2 shape, all users"""
+EVAL_SHAPES = {
+    # name: (test users, nitems, nfactors, positives per user)
+    "c2": (10_000, 5_000, 30, 5),              # BASELINE.json configs[1]: all users of the 10k x 5k problem
+    "large": (100_000, 1_000_000, 128, 10),    # 100k test users x 1M items (C5-shaped catalogue), k=128
+}
+
+
+def run_eval_ours(shape, device=0, reps=4):
+    """north_star part 3: all-item scoring (DMMA GEMM) fused with the rank statistics, device-resident factors"""
     import torch
     from qmf_b200 import capi
-    nu, ni, k, npos = 10_000, 5_000, 30, 5
+    nu, ni, k, npos = EVAL_SHAPES[shape]
+    kp = capi.check(capi.lib.qmfb_padded_k(k))
     dev = torch.device("cuda", device)
     g = torch.Generator(device=dev).manual_seed(3)
-    U = torch.rand(nu, k, generator=g, device=dev, dtype=torch.float64) - 0.5
-    V = torch.rand(ni, k, generator=g, device=dev, dtype=torch.float64) - 0.5
+    U = torch.zeros(nu, kp, device=dev, dtype=torch.float64)
+    V = torch.zeros(ni, kp, device=dev, dtype=torch.float64)
+    U[:, :k] = torch.rand(nu, k, generator=g, device=dev, dtype=torch.float64) - 0.5
+    V[:, :k] = torch.rand(ni, k, generator=g, device=dev, dtype=torch.float64) - 0.5
     bias = torch.rand(ni, generator=g, device=dev, dtype=torch.float64) - 0.5
     tu = torch.arange(nu, device=dev, dtype=torch.int32)
     lp = torch.arange(nu + 1, device=dev, dtype=torch.int64) * npos
-    li = (torch.sort(torch.rand(nu, ni, generator=g, device=dev).topk(npos, dim=1).indices, dim=1).values).to(torch.int32).reshape(-1).contiguous()
+    li = torch.sort(torch.randint(0, ni // npos, (nu, npos), generator=g, device=dev) +
+                    torch.arange(npos, device=dev) * (ni // npos), dim=1).values.to(torch.int32).reshape(-1).contiguous()
     cnt = torch.zeros(nu * npos + nu, device=dev, dtype=torch.int32)
     sc = torch.zeros(nu * npos, device=dev, dtype=torch.float64)
-    err = torch.zeros(1, device=dev, dtype=torch.int32)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     ms = []
-    for _ in range(4):
+    for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        capi.check(capi.lib.qmfb_eval_rank_dev(st, U.data_ptr(), k, V.data_ptr(), k, ni, k, bias.data_ptr(), tu.data_ptr(), nu,
-                                               lp.data_ptr(), li.data_ptr(), nu * npos, cnt.data_ptr(), sc.data_ptr(),
-                                               err.data_ptr()))
+        capi.check(capi.lib.qmfb_eval_rank_dev(st, U.data_ptr(), kp, V.data_ptr(), kp, ni, k, bias.data_ptr(), tu.data_ptr(), nu,
+                                               lp.data_ptr(), li.data_ptr(), nu * npos, npos, cnt.data_ptr(), sc.data_ptr()))
         b.record()
         torch.cuda.synchronize()
         ms.append(a.elapsed_time(b))
     t = min(ms[1:]) * 1e-3
     assert int(cnt.sum()) == nu * (ni - npos)
+    tf = 2.0 * nu * ni * k / t * 1e-12
     return {"shape": {"test_users": nu, "nitems": ni, "nfactors": k, "positives_per_user": npos}, "ms": t * 1e3,
-            "user_item_scores_per_s": nu * ni / t, "gflops": 2.0 * nu * ni * k / t * 1e-9,
-            "note": "exact-order FP64 mul+add (no FMA) so that scores are bit-identical to the reference; 3 launches "
-                    "(2 memsets + eval_rank_kernel, 4 users per CTA)"}
+            "user_item_scores_per_s": nu * ni / t, "tflops": tf,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64_peak_tflops(), "unit": "TFLOP/s",
+                         "frac": tf / fp64_peak_tflops(), "algorithmic_flops": 2.0 * nu * ni * k},
+            "note": "DMMA score GEMM fused with bucket counting; only pairs within the proven rounding bound of a "
+                    "positive's score are re-scored in the reference's exact order; 5 launches (2 memsets, item norms, "
+                    "positives, score kernel); algorithmic flops 2 nT ni k"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -379,8 +399,8 @@ def run_ours(args, cfg, workload):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
         "kernel": "wals_solve_kernel<16> (2 launches/epoch: user rows, item rows)",
-        "bound": "tensor", "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-        "frac": achieved_tf / FP64_PEAK_TFLOPS,
+        "bound": "tensor", "achieved": achieved_tf, "peak": fp64_peak_tflops(), "unit": "TFLOP/s",
+        "frac": achieved_tf / fp64_peak_tflops(),
         # dram__bytes_read.sum + dram__bytes_write.sum of the user-rows launch (profiles/r01_solve_final_ncu.csv:
         # 1.40 GB + 0.50 GB vs 1.71 GB algorithmic: the gathered item factors stay in L2); ncu reports no DRAM
         # counters for the item-rows launch of the same capture
@@ -465,7 +485,9 @@ def run_ours(args, cfg, workload):
             bpr[shape] = r
         if not args.no_cpu_baseline:
             bpr["cpu_baseline_c2"] = run_bpr_reference(os.cpu_count() or 1)
-    evalr = run_eval_ours(local_rank) if (rank == 0 and world == 1 and not args.no_bpr) else None
+    evalr = None
+    if rank == 0 and world == 1 and not args.no_bpr:
+        evalr = {shape: run_eval_ours(shape, local_rank) for shape in ("c2", "large")}
 
     if rank == 0:
         line = {

@@ -221,11 +221,36 @@ int64_t qmfb_bpr_launch_count(qmfb_bpr_t* h);
 int qmfb_eval_rank(int device, const double* U, int64_t nusers, const double* V, int64_t nitems, int k,
                    const double* biases, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
                    const int32_t* label_items, int32_t* cnt, double* pos_scores);
-/* same on device pointers (row strides ldu / ldv), asynchronous on `stream`; cnt must hold
- * label_ptr[nT] + nT ints, error is one int (bit 2 set: too many positives for one user) */
+/* The same on device pointers, asynchronous on `stream` (the kernel level): rows of U and V must be 16-byte
+ * aligned with an even stride >= qmfb_padded_k(k) and ZERO pad columns (the layout of the WALS engine's
+ * factor matrices); max_positives >= the largest label_ptr[t+1]-label_ptr[t] (pass nlabels if unknown);
+ * cnt holds nlabels + nT ints, pos_scores nlabels doubles.  Three steps: the positives' scores in the
+ * reference's exact order, sorted; all items by DMMA (a users x items GEMM tile by tile, fused with the
+ * bucket counting); only pairs whose DMMA score lies within a proven rounding bound of one of the user's
+ * positive scores are re-scored in the exact order - the counts are the reference's, bit for bit. */
 int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double* V, int64_t ldv, int64_t nitems, int k,
                        const double* biases, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
-                       const int32_t* label_items, int64_t nlabels, int32_t* cnt, double* pos_scores, int32_t* error);
+                       const int32_t* label_items, int64_t nlabels, int64_t max_positives, int32_t* cnt, double* pos_scores);
+/* The engines' evaluation on their RESIDENT factors (no host round trip of the factor matrices): host
+ * test-user arrays in, host counters out, as qmfb_eval_rank.  The sharded engine cuts the test users into
+ * one contiguous slice per GPU (test users are independent, every GPU holds full replicas); the counts
+ * do not depend on the cut. */
+int qmfb_wals_eval_rank(qmfb_wals_t* h, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
+                        const int32_t* label_items, int32_t* cnt, double* pos_scores);
+int qmfb_wals_sharded_eval_rank(qmfb_wals_sharded_t* h, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
+                                const int32_t* label_items, int32_t* cnt, double* pos_scores);
+int qmfb_bpr_eval_rank(qmfb_bpr_t* h, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
+                       const int32_t* label_items, int32_t* cnt, double* pos_scores);
+
+/* HOST side of the evaluation (no device work): the reference's metric arithmetic on the bucket counts.
+ * qmfb_repeated_add: s <- fl(s + t), `count` times, with the exact result of the one-by-one loop (the
+ * reference adds one equal term per negative when it accumulates AUC, qmf/metrics/Metrics.cpp:87-95) in
+ * O(binades crossed) steps.  qmfb_rank_metrics: per_user[t] = "auc" | "ap" | "p@K" | "r@K" of test user t
+ * from cnt (layout of qmfb_eval_rank), on `host_threads` threads (0 = all); QMFB_ERR_INVALID where the
+ * reference CHECK-fails (ap / r@K without a positive, K > nitems). */
+double qmfb_repeated_add(double s, double t, int64_t count);
+int qmfb_rank_metrics(const char* metric, const int32_t* cnt, const int64_t* label_ptr, int64_t nT, int64_t nitems, int host_threads,
+                      double* per_user);
 
 /* ---- dataset ingest on the GPU ------------------------------------------
  * Replaces IdIndex (qmf/utils/IdIndex.h) + WALSEngine::groupSignals / sortDataset

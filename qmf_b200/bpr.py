@@ -73,6 +73,11 @@ class BprEngineHandle:
         used = (n // nthreads) * nthreads
         return self.eval_loss_sum(u, i, j, used) / n
 
+    def eval_rank(self, test_users, label_ptr, label_items):
+        """ranking statistics of the test users on the RESIDENT factors and biases (qmfb_bpr_eval_rank)"""
+        from .wals import _eval_rank_call
+        return _eval_rank_call(lib.qmfb_bpr_eval_rank, self._h, test_users, label_ptr, label_items)
+
     def set_concurrency(self, max_pairs_in_flight):
         check(lib.qmfb_bpr_set_concurrency(self._h, int(max_pairs_in_flight)))
 

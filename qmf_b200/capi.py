@@ -99,8 +99,13 @@ _SIG = {
     "qmfb_bpr_launch_count": (c_i64, [vp]),
     "qmfb_eval_rank": (C.c_int, [C.c_int, p_f64, c_i64, p_f64, c_i64, C.c_int, vp, p_i32, c_i64, p_i64, p_i32, p_i32,
                                  p_f64]),
-    "qmfb_eval_rank_dev": (C.c_int, [vp, vp, c_i64, vp, c_i64, c_i64, C.c_int, vp, vp, c_i64, vp, vp, c_i64, vp, vp,
+    "qmfb_eval_rank_dev": (C.c_int, [vp, vp, c_i64, vp, c_i64, c_i64, C.c_int, vp, vp, c_i64, vp, vp, c_i64, c_i64, vp,
                                      vp]),
+    "qmfb_wals_eval_rank": (C.c_int, [vp, p_i32, c_i64, p_i64, p_i32, p_i32, p_f64]),
+    "qmfb_wals_sharded_eval_rank": (C.c_int, [vp, p_i32, c_i64, p_i64, p_i32, p_i32, p_f64]),
+    "qmfb_bpr_eval_rank": (C.c_int, [vp, p_i32, c_i64, p_i64, p_i32, p_i32, p_f64]),
+    "qmfb_repeated_add": (c_f64, [c_f64, c_f64, c_i64]),
+    "qmfb_rank_metrics": (C.c_int, [C.c_char_p, p_i32, p_i64, c_i64, c_i64, C.c_int, p_f64]),
     "qmfb_signals_build": (C.c_int, [C.c_int, c_i64, p_i64, p_i64, p_f64, C.POINTER(vp)]),
     "qmfb_signals_destroy": (C.c_int, [vp]),
     "qmfb_signals_device_ordinal": (C.c_int, [vp]),

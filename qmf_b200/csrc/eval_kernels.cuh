@@ -1,219 +1,391 @@
-// Ranking evaluation on the GPU (sm_100a): all-item scores of a test user fused with the rank
-// statistics that AUC / AP / P@k / R@k need, never materialising the nT x nitems score matrix.
-// Replaces
+// Ranking evaluation on the GPU (sm_100a): a users x items score GEMM on the FP64 tensor cores fused
+// with the per-user rank statistics that AUC / AP / P@k / R@k need; the nT x nitems score matrix is
+// never materialised.  Replaces
 //   Engine::computeTestScores                     qmf/Engine.cpp:73-96     (K7)
 //   AUC / Precision / Recall / AveragePrecision   qmf/metrics/Metrics.cpp:65-164 (K8, the sort)
 //
-// Exactness: a score is bias_i + sum_f U[u,f] * V[i,f] accumulated in f order with separately
-// rounded multiply and add (__dmul_rn / __dadd_rn, no FMA contraction) - bit-identical to the
-// reference compiled for x86-64 - so the ranking (every integer below) is bit-exact.
-//
-// Per test user t with positives P (test items with label > 0) and negatives N (all other
-// items, train positives included, Engine.cpp:58-69):
-//   sorted positives' scores ascending  s_(0) <= ... <= s_(nP-1)
+// What must be exact.  Per test user t with positives P (test items with label > 0) and negatives N
+// (all other items, train positives included, Engine.cpp:58-69) the metrics depend only on
 //   cnt[i], i = 0..nP  = #{ x in N : exactly i positives score strictly less than s_x }
-// Under the reference order (score descending, positives first on ties, Metrics.cpp:85-86) a
-// negative in bucket i is preceded by exactly nP - i positives, which is all that the metrics
-// use; the host turns cnt into AUC / AP / P@k / R@k with the reference's own arithmetic.
+// where s is the REFERENCE score: bias_i + sum_f U[u,f] * V[i,f] accumulated in f order with
+// separately rounded multiply and add (Engine.cpp:85-91).  Under the reference order (score
+// descending, positives first on ties, Metrics.cpp:85-86) a negative in bucket i is preceded by exactly
+// nP - i positives; the host turns cnt into AUC / AP / P@k / R@k with the reference's own arithmetic.
+//
+// How it is made fast AND exact (north_star part 3):
+//   1. eval_pos_kernel: the nP positives' scores of every test user in the reference's exact order
+//      (__dmul_rn / __dadd_rn, bit-identical), sorted ascending.
+//   2. eval_score_kernel: scores of ALL items by DMMA (mma.sync.m8n8k4.f64): a CTA keeps 64 users'
+//      factors in shared memory and streams item tiles through a cp.async ring.  A DMMA score s^ differs
+//      from the reference score s by at most
+//           eps = 4 (k + 4) 2^-53 (|bias| + ||u||_2 ||v||_2)
+//      (both are floating-point evaluations of the same k-term dot product: |s - S|, |s^ - S| <=
+//      gamma_{k+1} (|b| + sum |u_f v_f|), Cauchy-Schwarz, and a factor 2 of slack for the rounded norms).
+//      If no positive's exact score lies in [s^ - eps, s^ + eps] the bucket of the item is decided by
+//      s^ exactly as it would be by s.  Otherwise (a tie, a positive item itself, or a 1e-13 near-miss)
+//      the pair goes to a per-tile list and is re-scored in the reference's exact order.  Every integer
+//      is therefore the one the reference's sort would produce.
+//   3. the positives are taken out of their own buckets, the counts go to global memory.
+// Work units are (64 test users) x (an item range), dealt dynamically, so that a few hundred test
+// users still fill 148 SMs; counts of the item ranges of one user add up in global memory (integers:
+// deterministic).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace qmfb {
 
-constexpr int kEvalThreads = 512;
-constexpr int kEvalMaxPos = 2048;   // positives per test user held in shared memory
-constexpr int kEvalTileItems = 32;  // items scored per warp pass
+// D(8x8) += A(8x4) * B(4x8), FP64 (SASS: DMMA.8x8x4).  Lane T holds A[T/4][T%4], B[T%4][T/4], C[T/4][2*(T%4)+{0,1}].
+__device__ __forceinline__ void ev_dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+// 16-byte asynchronous copy global -> shared (SASS: LDGSTS), L1 bypass
+__device__ __forceinline__ void ev_cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
+               : "memory");
+}
+
+constexpr int kEvThreads = 256;
+constexpr int kEvU = 64;        // test users per work unit (8 DMMA row tiles)
+constexpr int kEvI = 64;        // items per tile
+constexpr int kEvKC = 32;       // factors per staged chunk
+constexpr int kEvLDB = kEvKC + 4;  // stage row stride in doubles: == 4 mod 16 -> conflict-free fragment loads
+constexpr int kEvSpCap = 2048;  // sorted positives' scores of one unit held in shared memory (else: global)
+constexpr int kEvPosSmem = 4096;  // eval_pos_kernel: positives of one user sorted in shared memory
 
 struct EvalParams {
-  const double* U;          // user factors, row stride ldu
+  const double* U;          // user factors, row stride ldu >= KP (KP = k rounded up to 32), pad columns zero
   int64_t ldu;
-  const double* V;          // item factors, row stride ldv
+  const double* V;          // item factors, row stride ldv >= KP, pad columns zero
   int64_t ldv;
   const double* bias;       // item biases or nullptr
-  int k;
+  int k, kp;
   int nitems;
   const int32_t* test_users;   // nT user idx
+  int nT;
   const int64_t* label_ptr;    // nT + 1: offsets into label_items and (shifted by t) into cnt
   const int32_t* label_items;  // per user: positive item idx, ascending
   int32_t* cnt;                // out: per user nP + 1 counters at offset label_ptr[t] + t (zeroed by the launcher)
   double* pos_scores;          // out: per user the positives' scores in ascending order (offset label_ptr[t])
-  int* error;                  // bit 2: a user has more than kEvalMaxPos positives
+  const double* vnorm;         // ||v_x||_2 per item
+  int nsplit;                  // item ranges per user group
+  int* unit_counter;           // dynamic unit scheduler
+  int stages;
+  int sort_in_kernel;          // 0: eval_pos_kernel leaves the scores unsorted (a segmented sort follows)
 };
 
-constexpr int kEvalFC = 16;     // factors per staged chunk
-constexpr int kEvalGroup = 4;   // test users scored together by a CTA: every staged item row is used kEvalGroup
-                                // times (less L2 traffic) and every lane runs kEvalGroup independent
-                                // multiply-add chains (the exact-order sum of one score is one dependent chain)
-
-__host__ __device__ inline size_t eval_smem_bytes(int k) {
-  const size_t pu = size_t(kEvalGroup) * size_t((k + 1) & ~1) * 8;
-  const size_t spos = size_t(kEvalGroup) * kEvalMaxPos * 8;
-  const size_t scnt = size_t(kEvalGroup) * (kEvalMaxPos + 2) * 4;
-  const size_t tiles = size_t(kEvalThreads / 32) * kEvalTileItems * (kEvalFC + 1) * 8;
-  return pu + spos + scnt + tiles;
+__host__ __device__ inline size_t eval_smem_bytes(int kp, int stages) {
+  size_t b = size_t(kEvU) * (kp + 4) * 8;              // U tile
+  b += size_t(stages) * kEvI * kEvLDB * 8;             // item chunk ring
+  b += size_t(kEvSpCap) * 8;                           // sorted positives
+  b += size_t(kEvSpCap + kEvU) * 4;                    // bucket counters
+  b += size_t(kEvU) * (8 + 8 + 4 + 4);                 // unorm, sp offset(int64), nP, user idx
+  b += size_t(kEvU) * kEvI * 2;                        // re-score list (uint16)
+  b += 64;                                             // list count, unit id, flags
+  return b;
 }
 
-__global__ void __launch_bounds__(kEvalThreads) eval_rank_kernel(const EvalParams prm, int nT) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: pu[G][kpad] | spos[G][kEvalMaxPos] | scnt[G][kEvalMaxPos + 2] (int) | tile[nwarps][32][kEvalFC + 1]
-  constexpr int G = kEvalGroup;
-  const int kpad = (prm.k + 1) & ~1;
-  double* pu = reinterpret_cast<double*>(smem_raw);
-  double* spos = pu + size_t(G) * kpad;
-  int* scnt = reinterpret_cast<int*>(spos + size_t(G) * kEvalMaxPos);
-  double* tiles = reinterpret_cast<double*>(scnt + size_t(G) * (kEvalMaxPos + 2));
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kEvalThreads / 32;
-  constexpr int ldt = kEvalFC + 1;  // odd stride: lanes reading one row each hit distinct banks
-  double* tile = tiles + size_t(warp) * kEvalTileItems * ldt;
-  const int ngroups = (nT + G - 1) / G;
+// ||v_x||_2 of every item row (one warp per row)
+__global__ void eval_item_norm_kernel(const double* __restrict__ V, int64_t ldv, int k, int nitems, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nw = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t x = w0; x < nitems; x += nw) {
+    double s = 0.0;
+    for (int f = lane; f < k; f += 32) {
+      const double v = V[x * ldv + f];
+      s = fma(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[x] = sqrt(s);
+  }
+}
 
-  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-    const int t0 = grp * G;
-    int nPg[G];
-    const int32_t* pos_items[G];
-    int64_t lp0g[G];
-    bool live[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int t = t0 + g;
-      live[g] = t < nT;
-      lp0g[g] = live[g] ? prm.label_ptr[t] : 0;
-      nPg[g] = live[g] ? int(prm.label_ptr[t + 1] - lp0g[g]) : 0;
-      pos_items[g] = prm.label_items + lp0g[g];
-      if (nPg[g] > kEvalMaxPos) {  // reported, user skipped (its counters stay zero)
-        if (tid == 0) atomicOr(prm.error, 4);
-        live[g] = false;
-        nPg[g] = 0;
+// the reference's score of (user row u, item x): Engine.cpp:85-91, bit-identical
+__device__ __forceinline__ double eval_exact_score(const double* __restrict__ u, const double* __restrict__ v, double b, int k) {
+  double s = b;
+  for (int f = 0; f < k; ++f) s = __dadd_rn(s, __dmul_rn(u[f], v[f]));
+  return s;
+}
+
+__device__ __forceinline__ int eval_lower_bound(const double* sp, int n, double s) {  // #{m : sp[m] < s}
+  int a = 0, b = n;
+  while (a < b) {
+    const int m = (a + b) >> 1;
+    if (sp[m] < s) a = m + 1; else b = m;
+  }
+  return a;
+}
+
+// ---- 1. positives: exact scores, sorted ascending, one CTA per test user (grid-stride) -------------
+__global__ void __launch_bounds__(256) eval_pos_kernel(const EvalParams prm) {
+  __shared__ double sp[kEvPosSmem];
+  const int tid = threadIdx.x;
+  for (int t = blockIdx.x; t < prm.nT; t += gridDim.x) {
+    const int64_t lp0 = prm.label_ptr[t];
+    const int nP = int(prm.label_ptr[t + 1] - lp0);
+    if (nP == 0) continue;
+    const double* u = prm.U + int64_t(prm.test_users[t]) * prm.ldu;
+    const bool in_smem = nP <= kEvPosSmem && prm.sort_in_kernel;
+    int n2 = 1;
+    while (n2 < nP) n2 <<= 1;
+    __syncthreads();  // previous user's sort is done with sp
+    for (int i = tid; i < (in_smem ? n2 : nP); i += blockDim.x) {
+      double s = __longlong_as_double(0x7ff0000000000000LL);  // +inf padding
+      if (i < nP) {
+        const int item = prm.label_items[lp0 + i];
+        s = eval_exact_score(u, prm.V + int64_t(item) * prm.ldv, prm.bias != nullptr ? prm.bias[item] : 0.0, prm.k);
       }
+      if (in_smem) sp[i] = s; else prm.pos_scores[lp0 + i] = s;
     }
-    __syncthreads();  // previous group done with shared memory
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int u = live[g] ? prm.test_users[t0 + g] : 0;
-      for (int f = tid; f < prm.k; f += kEvalThreads) pu[g * kpad + f] = live[g] ? prm.U[int64_t(u) * prm.ldu + f] : 0.0;
-    }
+    if (!in_smem) continue;  // sorted afterwards by a device-wide segmented sort
     __syncthreads();
-    // ---- scores of the positives, then sort ascending (bitonic, padded with +inf), user by user ----
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int nP = nPg[g];
-      double* sp = spos + size_t(g) * kEvalMaxPos;
-      int* sc = scnt + size_t(g) * (kEvalMaxPos + 2);
-      int n2 = 1;
-      while (n2 < nP) n2 <<= 1;
-      for (int i = tid; i < n2; i += kEvalThreads) {
-        double s = __longlong_as_double(0x7ff0000000000000LL);
-        if (i < nP) {
-          const int item = pos_items[g][i];
-          s = prm.bias != nullptr ? prm.bias[item] : 0.0;
-          const double* v = prm.V + int64_t(item) * prm.ldv;
-          for (int f = 0; f < prm.k; ++f) s = __dadd_rn(s, __dmul_rn(pu[g * kpad + f], v[f]));  // Engine.cpp:86-91
-        }
-        sp[i] = s;
-      }
-      for (int i = tid; i <= nP; i += kEvalThreads) sc[i] = 0;
-      __syncthreads();
-      for (int size = 2; size <= n2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-          for (int i = tid; i < n2; i += kEvalThreads) {
-            const int j = i ^ stride;
-            if (j > i) {
-              const double a = sp[i], b = sp[j];
-              const bool up = (i & size) == 0;
-              if ((a > b) == up) {
-                sp[i] = b;
-                sp[j] = a;
-              }
+    for (int size = 2; size <= n2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < n2; i += blockDim.x) {
+          const int j = i ^ stride;
+          if (j > i) {
+            const double a = sp[i], b = sp[j];
+            const bool up = (i & size) == 0;
+            if ((a > b) == up) {
+              sp[i] = b;
+              sp[j] = a;
             }
           }
-          __syncthreads();
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = tid; i < nP; i += blockDim.x) prm.pos_scores[lp0 + i] = sp[i];
+  }
+}
+
+// ---- 2. all items by DMMA + buckets -----------------------------------------------------------------
+__global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams prm) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int KP = prm.kp, LDU = KP + 4, NS = prm.stages;
+  double* utile = reinterpret_cast<double*>(smem);
+  double* ring = utile + size_t(kEvU) * LDU;
+  double* sps = ring + size_t(NS) * kEvI * kEvLDB;
+  int* cnts = reinterpret_cast<int*>(sps + kEvSpCap);
+  double* unorm = reinterpret_cast<double*>(cnts + kEvSpCap + kEvU);
+  int64_t* lp0s = reinterpret_cast<int64_t*>(unorm + kEvU);
+  int* nPs = reinterpret_cast<int*>(lp0s + kEvU);
+  int* soff = nPs + kEvU;                      // offset of the user's positives / counters in sps / cnts
+  uint16_t* list = reinterpret_cast<uint16_t*>(soff + kEvU);
+  int* misc = reinterpret_cast<int*>(list + kEvU * kEvI);  // [0] list count, [1] unit, [2] positives-in-smem flag
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int uh = warp & 1, iq = warp >> 1;     // users 32 uh .. +31 (4 row tiles), items 16 iq .. +15 (2 column tiles)
+  const int ngroups = (prm.nT + kEvU - 1) / kEvU;
+  const int nunits = ngroups * prm.nsplit;
+  const int nchunks = KP / kEvKC;
+  const double ceps = 4.0 * double(prm.k + 4) * 1.1102230246251565e-16;  // 4 (k + 4) 2^-53
+
+  for (;;) {
+    __syncthreads();  // everyone is done with the previous unit's shared memory
+    if (tid == 0) misc[1] = atomicAdd(prm.unit_counter, 1);
+    __syncthreads();
+    const int unit = misc[1];
+    if (unit >= nunits) break;
+    const int grp = unit / prm.nsplit, split = unit % prm.nsplit;
+    const int t0 = grp * kEvU, nU = min(kEvU, prm.nT - t0);
+    const int xb = int(int64_t(prm.nitems) * split / prm.nsplit), xe = int(int64_t(prm.nitems) * (split + 1) / prm.nsplit);
+
+    // ---- unit prologue: user rows, norms, positives, counters ------------------------------------------
+    if (tid < kEvU) {
+      const int64_t lp0 = tid < nU ? prm.label_ptr[t0 + tid] : 0;
+      lp0s[tid] = lp0;
+      nPs[tid] = tid < nU ? int(prm.label_ptr[t0 + tid + 1] - lp0) : -1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int off = 0;
+      for (int u = 0; u < kEvU; ++u) {
+        soff[u] = off;
+        off += max(nPs[u], 0) + 1;
+      }
+      misc[2] = (off <= kEvSpCap) ? 1 : 0;
+      misc[0] = 0;
+    }
+    {  // U tile: 16-byte cp.async, rows of users past the end are rows of the last valid user (never bucketed)
+      const int ppr = KP / 2;
+      for (int q = tid; q < kEvU * ppr; q += kEvThreads) {
+        const int r = q / ppr, piece = q % ppr;
+        const int t = t0 + min(r, nU - 1);
+        ev_cp_async16(utile + size_t(r) * LDU + piece * 2, prm.U + int64_t(prm.test_users[t]) * prm.ldu + piece * 2);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const bool in_smem = misc[2] != 0;
+    {  // ||u||_2 (4 threads per user), counters, sorted positives
+      const int r = tid >> 2, q = tid & 3;
+      double s = 0.0;
+      for (int f = q; f < prm.k; f += 4) {
+        const double v = utile[size_t(r) * LDU + f];
+        s = fma(v, v, s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0) unorm[r] = sqrt(s);
+      if (in_smem) {
+        for (int i = tid; i < kEvSpCap + kEvU; i += kEvThreads) cnts[i] = 0;
+        for (int u = 0; u < nU; ++u) {
+          for (int i = tid; i < nPs[u]; i += kEvThreads) sps[soff[u] + i] = prm.pos_scores[lp0s[u] + i];
         }
       }
     }
-    // ---- all items: exact scores for the G users, then bucket the negatives ---------------------------
-    // the staged tile is software-pipelined: the global loads of the NEXT (item pass, factor chunk)
-    // are in flight in registers while the current chunk is multiplied out of shared memory
-    constexpr int kPre = kEvalTileItems / 2;  // two item rows per load instruction (a half-warp each)
-    const int nchunks = (prm.k + kEvalFC - 1) / kEvalFC;
-    double pre[kPre];
-    auto fetch = [&](int x0, int fc) {
-      const int nf = min(kEvalFC, prm.k - fc);
+    __syncthreads();
+
+    // ---- item tiles ------------------------------------------------------------------------------------
+    const int ntiles = (xe - xb + kEvI - 1) / kEvI;
+    const int total = ntiles * nchunks;
+    auto issue = [&](int idx) {  // chunk idx = tile * nchunks + c
+      if (idx < total) {
+        const int tile = idx / nchunks, c = idx % nchunks;
+        double* st = ring + size_t(idx % NS) * kEvI * kEvLDB;
 #pragma unroll
-      for (int r = 0; r < kPre; ++r) {
-        const int xr = x0 + 2 * r + (lane >> 4), ff = lane & 15;
-        pre[r] = (xr < prm.nitems && ff < nf) ? prm.V[int64_t(xr) * prm.ldv + fc + ff] : 0.0;
+        for (int m = 0; m < (kEvI * kEvKC / 2) / kEvThreads; ++m) {
+          const int q = tid + kEvThreads * m, r = q / (kEvKC / 2), piece = q % (kEvKC / 2);
+          const int x = min(xb + tile * kEvI + r, prm.nitems - 1);
+          ev_cp_async16(st + r * kEvLDB + piece * 2, prm.V + int64_t(x) * prm.ldv + c * kEvKC + piece * 2);
+        }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");  // always: uniform group accounting
     };
-    if (warp * kEvalTileItems < prm.nitems) fetch(warp * kEvalTileItems, 0);
-    for (int x0 = warp * kEvalTileItems; x0 < prm.nitems; x0 += nwarps * kEvalTileItems) {
-      const int x = x0 + lane;
-      const double b0 = (x < prm.nitems && prm.bias != nullptr) ? prm.bias[x] : 0.0;
-      double s[G];
+    for (int i = 0; i < NS - 1; ++i) issue(i);
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int x0 = xb + tile * kEvI;
+      double acc[4][2][2];
 #pragma unroll
-      for (int g = 0; g < G; ++g) s[g] = b0;
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+      // this lane's 4 item columns: norms and biases for the epilogue (loaded early, used late)
+      double vn[2][2], vb[2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int x = x0 + 16 * iq + 8 * nt + 2 * (lane & 3) + e;
+          const bool ok = x < xe;
+          vn[nt][e] = ok ? __ldg(prm.vnorm + x) : 0.0;
+          vb[nt][e] = (ok && prm.bias != nullptr) ? __ldg(prm.bias + x) : 0.0;
+        }
       for (int c = 0; c < nchunks; ++c) {
-        const int fc = c * kEvalFC, nf = min(kEvalFC, prm.k - fc);
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < kPre; ++r) tile[(2 * r + (lane >> 4)) * ldt + (lane & 15)] = pre[r];
-        __syncwarp();
-        if (c + 1 < nchunks) {
-          fetch(x0, fc + kEvalFC);
-        } else if (x0 + nwarps * kEvalTileItems < prm.nitems) {
-          fetch(x0 + nwarps * kEvalTileItems, 0);
+        const int idx = tile * nchunks + c;
+        if (NS == 4) {
+          asm volatile("cp.async.wait_group 2;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
         }
-        if (x < prm.nitems) {
-          const double* row = tile + lane * ldt;
-          const double* pf = pu + fc;
-          for (int f = 0; f < nf; ++f) {
-            const double v = row[f];
+        __syncthreads();  // chunk idx landed for everyone; the stage consumed in the previous iteration is free
+        issue(idx + NS - 1);
+        const double* st = ring + size_t(idx % NS) * kEvI * kEvLDB + size_t(16 * iq + (lane >> 2)) * kEvLDB + (lane & 3);
+        const double* ua = utile + size_t(32 * uh + (lane >> 2)) * LDU + c * kEvKC + (lane & 3);
 #pragma unroll
-            for (int g = 0; g < G; ++g) s[g] = __dadd_rn(s[g], __dmul_rn(pf[g * kpad + f], v));
+        for (int s = 0; s < kEvKC / 4; ++s) {
+          double a[4], b[2];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) a[mt] = ua[size_t(8 * mt) * LDU + 4 * s];
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) b[nt] = st[8 * nt * kEvLDB + 4 * s];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) ev_dmma(acc[mt][nt], a[mt], b[nt]);
+        }
+      }
+      // ---- epilogue: bucket the 16 scores of this lane --------------------------------------------------
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const int ul = 32 * uh + 8 * mt + (lane >> 2);
+        const int nP = nPs[ul];
+        if (nP < 0) continue;
+        const double un = unorm[ul];
+        const double* sp = in_smem ? sps + soff[ul] : prm.pos_scores + lp0s[ul];
+        int* cn = in_smem ? cnts + soff[ul] : prm.cnt + lp0s[ul] + (t0 + ul);
+        double lo[4], hi[4];
+        int a[4], b[4];
+        bool live[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int nt = q >> 1, e = q & 1;
+          const double s = acc[mt][nt][e] + vb[nt][e];
+          const double eps = ceps * (fabs(vb[nt][e]) + un * vn[nt][e]);
+          lo[q] = s - eps;
+          hi[q] = s + eps;
+          a[q] = 0;
+          b[q] = nP;
+          live[q] = (x0 + 16 * iq + 8 * nt + 2 * (lane & 3) + e) < xe;
+        }
+        // four lower_bound(sp, lo) searches in lockstep (independent loads in flight)
+        for (int span = nP; span > 0; span >>= 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (a[q] < b[q]) {
+              const int m = (a[q] + b[q]) >> 1;
+              if (sp[m] < lo[q]) a[q] = m + 1; else b[q] = m;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (!live[q]) continue;
+          if (a[q] < nP && sp[a[q]] <= hi[q]) {
+            // a positive's score within the error bound: re-score this pair in the reference's exact order
+            const int xl = 16 * iq + 8 * (q >> 1) + 2 * (lane & 3) + (q & 1);
+            list[atomicAdd(&misc[0], 1)] = uint16_t((ul << 8) | xl);
+          } else {
+            atomicAdd(cn + a[q], 1);
           }
         }
       }
-      // Bucket EVERY item as if it were a negative (the positives are taken out again after the loop:
-      // no membership test in the hot loop); lanes with the same bucket share one shared-memory atomic.
-      const unsigned act = __ballot_sync(0xffffffffu, x < prm.nitems);
-      if (x < prm.nitems) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          if (!live[g]) continue;
-          const double* sp = spos + size_t(g) * kEvalMaxPos;
-          int a = 0, b = nPg[g];  // number of positives scoring strictly less than s
-          while (a < b) {
-            const int m = (a + b) >> 1;
-            if (sp[m] < s[g]) a = m + 1; else b = m;
-          }
-          const unsigned same = __match_any_sync(act, a);
-          if (lane == __ffs(same) - 1) atomicAdd(&scnt[size_t(g) * (kEvalMaxPos + 2) + a], __popc(same));
+      __syncthreads();
+      const int nlist = misc[0];
+      if (nlist > 0) {
+        for (int e = tid; e < nlist; e += kEvThreads) {
+          const int ul = list[e] >> 8, x = x0 + (list[e] & 255);
+          const double s = eval_exact_score(utile + size_t(ul) * LDU, prm.V + int64_t(x) * prm.ldv,
+                                            prm.bias != nullptr ? prm.bias[x] : 0.0, prm.k);
+          const double* sp = in_smem ? sps + soff[ul] : prm.pos_scores + lp0s[ul];
+          int* cn = in_smem ? cnts + soff[ul] : prm.cnt + lp0s[ul] + (t0 + ul);
+          atomicAdd(cn + eval_lower_bound(sp, nPs[ul], s), 1);
         }
+        __syncthreads();
+        if (tid == 0) misc[0] = 0;
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- the positive ITEMS of this item range were bucketed like negatives: take them out again ----------
+    // (a positive's own exact score is an entry of its sorted list, so its bucket is lower_bound of that score)
+    for (int ul = 0; ul < nU; ++ul) {
+      const int nP = nPs[ul];
+      const double* sp = in_smem ? sps + soff[ul] : prm.pos_scores + lp0s[ul];
+      int* cn = in_smem ? cnts + soff[ul] : prm.cnt + lp0s[ul] + (t0 + ul);
+      for (int i = tid; i < nP; i += kEvThreads) {
+        const int item = prm.label_items[lp0s[ul] + i];
+        if (item < xb || item >= xe) continue;
+        const double s = eval_exact_score(utile + size_t(ul) * LDU, prm.V + int64_t(item) * prm.ldv,
+                                          prm.bias != nullptr ? prm.bias[item] : 0.0, prm.k);
+        atomicSub(cn + eval_lower_bound(sp, nP, s), 1);
       }
     }
     __syncthreads();
-    // a positive item's own score is bit-identical to its entry in spos, so the bucket it was counted
-    // in above is lower_bound(spos, that score): take the nP positives out again
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const double* sp = spos + size_t(g) * kEvalMaxPos;
-      for (int i = tid; i < nPg[g]; i += kEvalThreads) {
-        const double v = sp[i];
-        int a = 0, b = nPg[g];
-        while (a < b) {
-          const int m = (a + b) >> 1;
-          if (sp[m] < v) a = m + 1; else b = m;
+    if (in_smem) {  // counters of this unit -> global (the item ranges of one user add up)
+      for (int ul = 0; ul < nU; ++ul) {
+        int32_t* out = prm.cnt + lp0s[ul] + (t0 + ul);
+        for (int i = tid; i <= nPs[ul]; i += kEvThreads) {
+          const int v = cnts[soff[ul] + i];
+          if (v != 0) atomicAdd(out + i, v);
         }
-        atomicSub(&scnt[size_t(g) * (kEvalMaxPos + 2) + a], 1);
       }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      if (!live[g]) continue;
-      const int t = t0 + g;
-      for (int i = tid; i <= nPg[g]; i += kEvalThreads) prm.cnt[lp0g[g] + t + i] = scnt[size_t(g) * (kEvalMaxPos + 2) + i];
-      for (int i = tid; i < nPg[g]; i += kEvalThreads) prm.pos_scores[lp0g[g] + i] = spos[size_t(g) * kEvalMaxPos + i];
     }
   }
 }

@@ -1,7 +1,6 @@
-// C-ABI (include/qmf_b200.h) for BPR Hogwild SGD and the ranking evaluation.
+// C-ABI (include/qmf_b200.h) for BPR Hogwild SGD (the ranking evaluation is qmfb_eval.cu).
 #include "qmfb_common.h"
 #include "bpr_kernels.cuh"
-#include "eval_kernels.cuh"
 
 #include <algorithm>
 #include <numeric>
@@ -358,83 +357,17 @@ int qmfb_bpr_last_epoch_ms(qmfb_bpr_t* h, float* ms) {
   *ms = h->epoch_ms;
   return QMFB_OK;
 }
+int qmfb_bpr_eval_rank(qmfb_bpr_t* h, const int32_t* test_users, int64_t nT, const int64_t* label_ptr, const int32_t* label_items,
+                       int32_t* cnt, double* pos_scores) {
+  if (!h) return set_error(QMFB_ERR_INVALID, "qmfb_bpr_eval_rank: null handle");
+  QMFB_CUDA(cudaSetDevice(h->device));
+  QMFB_CUDA(cudaStreamSynchronize(h->stream));
+  return eval_rank_resident(h->device, h->F[0], h->k, h->n[0], h->F[1], h->k, h->n[1], h->k, h->use_biases ? h->bias : nullptr,
+                            test_users, nT, label_ptr, label_items, cnt, pos_scores);
+}
+
 double* qmfb_bpr_factors_device(qmfb_bpr_t* h, int side) { return (h && side >= 0 && side <= 1) ? h->F[side] : nullptr; }
 double* qmfb_bpr_biases_device(qmfb_bpr_t* h) { return h ? h->bias : nullptr; }
 int64_t qmfb_bpr_launch_count(qmfb_bpr_t* h) { return h ? h->launches : 0; }
-
-// ------------------------------------------------------------------------------------------
-// ranking evaluation
-// ------------------------------------------------------------------------------------------
-int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double* V, int64_t ldv, int64_t nitems, int k,
-                       const double* biases, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
-                       const int32_t* label_items, int64_t nlabels, int32_t* cnt, double* pos_scores, int32_t* error) {
-  if (!U || !V || !test_users || !label_ptr || !cnt || !pos_scores || !error || nT < 0 || nitems < 1 || nitems > INT32_MAX ||
-      k < 1 || nT > INT32_MAX) {
-    return set_error(QMFB_ERR_INVALID, "qmfb_eval_rank_dev: bad argument");
-  }
-  auto st = static_cast<cudaStream_t>(stream);
-  const size_t smem = eval_smem_bytes(k);
-  // per device / context attribute: set on every call (cheap), a process may use several devices
-  QMFB_CUDA(cudaFuncSetAttribute(eval_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  if (smem > 200 * 1024) return set_error(QMFB_ERR_UNSUPPORTED, "nfactors too large for the evaluation kernel");
-  QMFB_CUDA(cudaMemsetAsync(error, 0, sizeof(int32_t), st));
-  QMFB_CUDA(cudaMemsetAsync(cnt, 0, size_t(nlabels + nT) * sizeof(int32_t), st));
-  if (nT == 0) return QMFB_OK;
-  EvalParams p{U, ldu, V, ldv, biases, k, int(nitems), test_users, label_ptr, label_items, cnt, pos_scores, error};
-  int dev = 0, sms = 148;
-  QMFB_CUDA(cudaGetDevice(&dev));
-  QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t ngroups = (nT + kEvalGroup - 1) / kEvalGroup;
-  const int blocks = int(std::min<int64_t>(ngroups, int64_t(sms) * 2));
-  eval_rank_kernel<<<blocks, kEvalThreads, smem, st>>>(p, int(nT));
-  QMFB_CUDA(cudaGetLastError());
-  return QMFB_OK;
-}
-
-int qmfb_eval_rank(int device, const double* U, int64_t nusers, const double* V, int64_t nitems, int k,
-                   const double* biases, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
-                   const int32_t* label_items, int32_t* cnt, double* pos_scores) {
-  if (!U || !V || !test_users || !label_ptr || !cnt || nT < 0 || nusers < 1) return set_error(QMFB_ERR_INVALID, "qmfb_eval_rank: bad argument");
-  const int64_t nl = label_ptr[nT];
-  for (int64_t t = 0; t < nT; ++t) {
-    if (test_users[t] < 0 || test_users[t] >= nusers) return set_error(QMFB_ERR_INVALID, "qmfb_eval_rank: test user %lld out of range", (long long)t);
-    for (int64_t q = label_ptr[t]; q < label_ptr[t + 1]; ++q) {
-      if (label_items[q] < 0 || label_items[q] >= nitems || (q > label_ptr[t] && label_items[q] <= label_items[q - 1])) {
-        return set_error(QMFB_ERR_INVALID, "qmfb_eval_rank: label items of user %lld must be ascending, distinct and in range", (long long)t);
-      }
-    }
-  }
-  QMFB_CUDA(cudaSetDevice(device));
-  double *dU = nullptr, *dV = nullptr, *dB = nullptr, *dS = nullptr;
-  int32_t *dT = nullptr, *dL = nullptr, *dC = nullptr, *dE = nullptr;
-  int64_t* dP = nullptr;
-  int rc = [&]() -> int {
-    QMFB_CUDA(cudaMalloc(&dU, size_t(nusers) * k * 8));
-    QMFB_CUDA(cudaMalloc(&dV, size_t(nitems) * k * 8));
-    if (biases) QMFB_CUDA(cudaMalloc(&dB, size_t(nitems) * 8));
-    QMFB_CUDA(cudaMalloc(&dS, size_t(std::max<int64_t>(nl, 1)) * 8));
-    QMFB_CUDA(cudaMalloc(&dT, size_t(std::max<int64_t>(nT, 1)) * 4));
-    QMFB_CUDA(cudaMalloc(&dL, size_t(std::max<int64_t>(nl, 1)) * 4));
-    QMFB_CUDA(cudaMalloc(&dC, size_t(nl + nT + 1) * 4));
-    QMFB_CUDA(cudaMalloc(&dE, 4));
-    QMFB_CUDA(cudaMalloc(&dP, size_t(nT + 1) * 8));
-    QMFB_CUDA(cudaMemcpy(dU, U, size_t(nusers) * k * 8, cudaMemcpyHostToDevice));
-    QMFB_CUDA(cudaMemcpy(dV, V, size_t(nitems) * k * 8, cudaMemcpyHostToDevice));
-    if (biases) QMFB_CUDA(cudaMemcpy(dB, biases, size_t(nitems) * 8, cudaMemcpyHostToDevice));
-    QMFB_CUDA(cudaMemcpy(dT, test_users, size_t(nT) * 4, cudaMemcpyHostToDevice));
-    if (nl > 0) QMFB_CUDA(cudaMemcpy(dL, label_items, size_t(nl) * 4, cudaMemcpyHostToDevice));
-    QMFB_CUDA(cudaMemcpy(dP, label_ptr, size_t(nT + 1) * 8, cudaMemcpyHostToDevice));
-    int r = qmfb_eval_rank_dev(nullptr, dU, k, dV, k, nitems, k, dB, dT, nT, dP, dL, nl, dC, dS, dE);
-    if (r) return r;
-    int32_t err = 0;
-    QMFB_CUDA(cudaMemcpy(&err, dE, 4, cudaMemcpyDeviceToHost));
-    if (err & 4) return set_error(QMFB_ERR_UNSUPPORTED, "a test user has more than %d positive items", kEvalMaxPos);
-    QMFB_CUDA(cudaMemcpy(cnt, dC, size_t(nl + nT) * 4, cudaMemcpyDeviceToHost));
-    if (pos_scores && nl > 0) QMFB_CUDA(cudaMemcpy(pos_scores, dS, size_t(nl) * 8, cudaMemcpyDeviceToHost));
-    return QMFB_OK;
-  }();
-  cudaFree(dU); cudaFree(dV); cudaFree(dB); cudaFree(dS); cudaFree(dT); cudaFree(dL); cudaFree(dC); cudaFree(dE); cudaFree(dP);
-  return rc;
-}
 
 }  // extern "C"

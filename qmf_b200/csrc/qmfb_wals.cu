@@ -604,6 +604,15 @@ int qmfb_wals_epoch_host(qmfb_wals_t* h, double alpha, double lambda, const doub
   return QMFB_OK;
 }
 
+int qmfb_wals_eval_rank(qmfb_wals_t* h, const int32_t* test_users, int64_t nT, const int64_t* label_ptr, const int32_t* label_items,
+                        int32_t* cnt, double* pos_scores) {
+  if (!h) return set_error(QMFB_ERR_INVALID, "qmfb_wals_eval_rank: null handle");
+  QMFB_CUDA(cudaSetDevice(h->device));
+  QMFB_CUDA(cudaStreamSynchronize(h->stream));
+  return eval_rank_resident(h->device, h->F[0], h->kp, h->n[0], h->F[1], h->kp, h->n[1], h->k, nullptr, test_users, nT, label_ptr,
+                            label_items, cnt, pos_scores);
+}
+
 double* qmfb_wals_factors_device(qmfb_wals_t* h, int side) { return (h && side >= 0 && side <= 1) ? h->F[side] : nullptr; }
 void* qmfb_wals_stream(qmfb_wals_t* h) { return h ? h->stream : nullptr; }
 int64_t qmfb_wals_launch_count(qmfb_wals_t* h) { return h ? h->launches : 0; }

@@ -463,6 +463,22 @@ int qmfb_wals_sharded_epoch_host(qmfb_wals_sharded_t* h, double alpha, double la
   return QMFB_OK;
 }
 
+int qmfb_wals_sharded_eval_rank(qmfb_wals_sharded_t* h, const int32_t* test_users, int64_t nT, const int64_t* label_ptr,
+                                const int32_t* label_items, int32_t* cnt, double* pos_scores) {
+  if (!h) return set_error(QMFB_ERR_INVALID, "qmfb_wals_sharded_eval_rank: null handle");
+  std::vector<int> devices;
+  std::vector<const double*> U, V;
+  for (auto& s : h->sh) {
+    QMFB_CUDA(cudaSetDevice(s.device));
+    QMFB_CUDA(cudaStreamSynchronize(s.stream));
+    devices.push_back(s.device);
+    U.push_back(s.F[0]);
+    V.push_back(s.F[1]);
+  }
+  return eval_rank_sharded(h->ndev, devices.data(), U.data(), h->kp, h->n[0], V.data(), h->kp, h->n[1], h->k, test_users, nT, label_ptr,
+                           label_items, cnt, pos_scores);
+}
+
 double* qmfb_wals_sharded_factors_device(qmfb_wals_sharded_t* h, int side, int slot) {
   return (h && side >= 0 && side <= 1 && slot >= 0 && slot < h->ndev) ? h->sh[size_t(slot)].F[side] : nullptr;
 }

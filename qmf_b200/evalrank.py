@@ -51,8 +51,8 @@ def user_metrics(cnt_t, nitems, names):
             auc = 0.0
             for i in range(nP, -1, -1):
                 term = float(nP - i) / nP / nN
-                for _ in range(int(cnt_t[i])):
-                    auc += term
+                # cnt additions of the same term, exact result of the one-by-one loop
+                auc = float(lib.qmfb_repeated_add(auc, term, int(cnt_t[i])))
             out[name] = auc
         elif name == "ap":
             ap = 0.0
@@ -85,3 +85,12 @@ def average_metric(values, nthreads):
             part = part + values[t]
         total = total + part
     return total / n
+
+
+def rank_metrics(name, cnt, label_ptr, nitems, host_threads=0):
+    """per-user values of one ranking metric for ALL test users at once (qmfb_rank_metrics, host threads)"""
+    lp = np.ascontiguousarray(label_ptr, dtype=np.int64)
+    c = np.ascontiguousarray(cnt, dtype=np.int32)
+    out = np.empty(len(lp) - 1, dtype=np.float64)
+    check(lib.qmfb_rank_metrics(name.encode(), c, lp, len(lp) - 1, int(nitems), host_threads, out))
+    return out

@@ -26,49 +26,70 @@ void Engine::initAvgTestData(TestData& out, const std::vector<DatasetElem>& test
     std::shuffle(out.users.begin(), out.users.end(), std::mt19937(seed));
     out.users.resize(numTestUsers);
   }
-  std::unordered_map<size_t, size_t> slot;
-  for (size_t t = 0; t < out.users.size(); ++t) slot[out.users[t]] = t;
-  // last value wins per (user, item); positive <=> value > 0 (Metrics.cpp:72)
-  std::vector<std::unordered_map<int32_t, Double>> labels(out.users.size());
-  for (const auto& e : testDataset) {
-    const size_t u = userIndex.idx(e.userId), p = itemIndex.idx(e.itemId);
-    if (u == IdIndex::missingIdx || p == IdIndex::missingIdx) continue;
-    const auto it = slot.find(u);
-    if (it != slot.end()) labels[it->second][int32_t(p)] = e.value;
+  // slot of a user idx in `users` (dense table instead of the reference's unordered_map, Engine.cpp:53-60)
+  std::vector<int64_t> slot(userIndex.size(), -1);
+  for (size_t t = 0; t < out.users.size(); ++t) slot[out.users[t]] = int64_t(t);
+  // The reference writes testLabels[slot][item] = value line by line into dense nT x nitems vectors
+  // (Engine.cpp:62-70): the LAST line of a (user, item) wins, positive <=> value > 0 (Metrics.cpp:72).
+  // Same result without dense rows or per-user hash maps: the valid lines as (slot, item, line) keys,
+  // sorted; the last line of each (slot, item) run decides.
+  struct Cell {
+    int64_t slot;
+    int32_t item;
+    uint32_t hi;   // line number (split so that the struct stays 24 bytes)
+    uint32_t lo;
+    Double value;
+  };
+  std::vector<Cell> cells;
+  for (size_t p = 0; p < testDataset.size(); ++p) {
+    const auto& e = testDataset[p];
+    const size_t u = userIndex.idx(e.userId), i = itemIndex.idx(e.itemId);
+    if (u == IdIndex::missingIdx || i == IdIndex::missingIdx || slot[u] < 0) continue;
+    cells.push_back(Cell{slot[u], int32_t(i), uint32_t(uint64_t(p) >> 32), uint32_t(p), e.value});
   }
-  out.labelPtr.assign(1, 0);
+  std::sort(cells.begin(), cells.end(), [](const Cell& a, const Cell& b) {
+    if (a.slot != b.slot) return a.slot < b.slot;
+    if (a.item != b.item) return a.item < b.item;
+    return (uint64_t(a.hi) << 32 | a.lo) < (uint64_t(b.hi) << 32 | b.lo);
+  });
+  out.labelPtr.assign(out.users.size() + 1, 0);
   out.labelItems.clear();
-  for (const auto& row : labels) {
-    const size_t begin = out.labelItems.size();
-    for (const auto& kv : row) {
-      if (kv.second > 0.0) out.labelItems.push_back(kv.first);
+  for (size_t p = 0; p < cells.size(); ++p) {
+    const bool last = p + 1 == cells.size() || cells[p + 1].slot != cells[p].slot || cells[p + 1].item != cells[p].item;
+    if (last && cells[p].value > 0.0) {
+      out.labelItems.push_back(cells[p].item);
+      ++out.labelPtr[size_t(cells[p].slot) + 1];
     }
-    std::sort(out.labelItems.begin() + begin, out.labelItems.end());
-    out.labelPtr.push_back(int64_t(out.labelItems.size()));
   }
+  for (size_t t = 0; t < out.users.size(); ++t) out.labelPtr[t + 1] += out.labelPtr[t];
 }
 
-void Engine::computeAndRecordTestAvgMetrics(MetricsEngine& metrics, size_t epoch, const TestData& test,
-                                            const FactorData& userFactors, const FactorData& itemFactors,
-                                            size_t nthreads, int device) {
-  const size_t nT = test.users.size(), nItems = itemFactors.nelems();
+void Engine::computeAndRecordTestAvgMetrics(MetricsEngine& metrics, size_t epoch, const TestData& test, size_t nItems,
+                                            size_t nthreads, const RankFn& rank) {
+  const size_t nT = test.users.size();
   std::vector<int32_t> users(nT);
   for (size_t t = 0; t < nT; ++t) users[t] = int32_t(test.users[t]);
   std::vector<int32_t> cnt(test.labelItems.size() + nT, 0);
   std::vector<Double> posScores(std::max<size_t>(test.labelItems.size(), 1));
-  const int rc = qmfb_eval_rank(device, userFactors.getFactors().data(), int64_t(userFactors.nelems()),
-                                itemFactors.getFactors().data(), int64_t(nItems), int(userFactors.nfactors()),
-                                itemFactors.withBiases() ? itemFactors.getBiases().data() : nullptr, users.data(),
-                                int64_t(nT), test.labelPtr.data(), test.labelItems.data(), cnt.data(), posScores.data());
-  CHECK_EQ(rc, 0) << "qmfb_eval_rank: " << qmfb_last_error();
+  // all-item scores + rank statistics on the GPU, against the engine's RESIDENT factors
+  const int rc = rank(users.data(), int64_t(nT), test.labelPtr.data(), test.labelItems.data(), cnt.data(), posScores.data());
+  CHECK_EQ(rc, 0) << "ranking evaluation: " << qmfb_last_error();
   for (const auto& name : metrics.testAvgMetrics()) {
     MetricSpec spec;
     CHECK(MetricsManager::get().lookup(name, spec)) << "missing metric test_avg_" << name;
     std::vector<Double> perUser(nT);
-    for (size_t t = 0; t < nT; ++t) {
-      const size_t nPos = size_t(test.labelPtr[t + 1] - test.labelPtr[t]);
-      perUser[t] = computeMetricFromCounts(spec, cnt.data() + test.labelPtr[t] + int64_t(t), nPos, nItems);
-    }
+    // per-user values on all host threads (independent users); the average keeps the reference's order
+    const size_t nth = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), nT / 512 + 1));
+    auto work = [&](size_t th) {
+      for (size_t t = nT * th / nth, e = nT * (th + 1) / nth; t < e; ++t) {
+        const size_t nPos = size_t(test.labelPtr[t + 1] - test.labelPtr[t]);
+        perUser[t] = computeMetricFromCounts(spec, cnt.data() + test.labelPtr[t] + int64_t(t), nPos, nItems);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (size_t th = 1; th < nth; ++th) pool.emplace_back(work, th);
+    work(0);
+    for (auto& th : pool) th.join();
     metrics.recordMetric("test_avg_" + name, epoch, averageOverUsers(perUser, nthreads));
   }
 }

@@ -3,6 +3,7 @@
 // user (the reference materialises dense nT x nitems label and score matrices, Engine.cpp:52-69;
 // the GPU path never needs them).
 #pragma once
+#include <functional>
 #include <memory>
 #include <ostream>
 #include <string>
@@ -43,11 +44,13 @@ class Engine {
   static void initAvgTestData(TestData& out, const std::vector<DatasetElem>& testDataset, const IdIndex& userIndex,
                               const IdIndex& itemIndex, size_t numTestUsers = 0, int32_t seed = 0);
 
-  // scores of every item for every test user + rank statistics on the GPU (qmfb_eval_rank), then
-  // every requested test-average metric recorded with the reference's averaging order
-  static void computeAndRecordTestAvgMetrics(MetricsEngine& metrics, size_t epoch, const TestData& test,
-                                             const FactorData& userFactors, const FactorData& itemFactors,
-                                             size_t nthreads, int device);
+  // scores of every item for every test user + rank statistics on the GPU, then every requested
+  // test-average metric recorded with the reference's averaging order.  `rank` runs the engine's
+  // qmfb_*_eval_rank on its resident factors (signature of qmfb_wals_eval_rank without the handle).
+  using RankFn = std::function<int(const int32_t* users, int64_t nT, const int64_t* labelPtr, const int32_t* labelItems,
+                                   int32_t* cnt, double* posScores)>;
+  static void computeAndRecordTestAvgMetrics(MetricsEngine& metrics, size_t epoch, const TestData& test, size_t nItems,
+                                             size_t nthreads, const RankFn& rank);
 
   // "<id>[ <bias>] <f0> ... <fk-1>\n", fixed, 9 decimals (qmf/Engine.cpp:98-122)
   static void saveFactors(const FactorData& factorData, const IdIndex& index, const std::string& fileName);

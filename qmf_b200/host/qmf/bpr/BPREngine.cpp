@@ -140,8 +140,10 @@ void BPREngine::evaluate(const size_t epoch) {
   LOG(INFO) << "epoch " << epoch << ": train loss = " << lastTrainLoss_ << ", test loss = " << lastTestLoss_;
   if (metricsEngine_ && !metricsEngine_->testAvgMetrics().empty() && !test_.empty() &&
       (metricsEngine_->config().alwaysCompute || epoch == config_.nepochs)) {
-    syncFactorsToHost();
-    computeAndRecordTestAvgMetrics(*metricsEngine_, epoch, test_, *userFactors_, *itemFactors_, nthreads_, config_.device);
+    computeAndRecordTestAvgMetrics(*metricsEngine_, epoch, test_, nitems(), nthreads_,
+                                   [this](const int32_t* users, int64_t nT, const int64_t* lp, const int32_t* li, int32_t* cnt, double* ps) {
+                                     return qmfb_bpr_eval_rank(dev_, users, nT, lp, li, cnt, ps);
+                                   });
   }
 }
 

@@ -6,6 +6,8 @@
 
 #include <qmf/utils/Log.h>
 
+#include "qmf_b200.h"
+
 namespace qmf {
 
 namespace detail {
@@ -70,7 +72,8 @@ Double computeMetricFromCounts(const MetricSpec& spec, const int32_t* cnt, size_
     Double auc = 0;
     for (size_t i = nPos + 1; i-- > 0;) {
       const Double term = static_cast<Double>(int(nPos - i)) / p / n;
-      for (int32_t c = 0; c < cnt[i]; ++c) auc += term;
+      // cnt[i] additions of the same term, with the exact result of the one-by-one loop (qmfb_repeated_add)
+      auc = qmfb_repeated_add(auc, term, cnt[i]);
     }
     return auc;
   }

@@ -28,6 +28,7 @@ WALSEngine::WALSEngine(const WALSConfig& config, const std::unique_ptr<MetricsEn
 
 WALSEngine::~WALSEngine() {
   if (dev_ != nullptr) qmfb_wals_destroy(dev_);
+  if (sharded_ != nullptr) qmfb_wals_sharded_destroy(sharded_);
 }
 
 void WALSEngine::init(const std::vector<DatasetElem>& dataset) {
@@ -78,6 +79,18 @@ void WALSEngine::init(const std::vector<DatasetElem>& dataset) {
     itemFactors_->setFactors(config_.DistributionFile);
   }
 
+  if (config_.ngpus > 1) {
+    // users and items row-partitioned over the GPUs of this box, full factor replicas on each
+    // (SURVEY.md 8e); factors and loss are bit-identical to the one-GPU engine
+    std::vector<int> devices(size_t(config_.ngpus));
+    for (int d = 0; d < config_.ngpus; ++d) devices[size_t(d)] = config_.device + d;
+    QMFB_OK_OR_DIE(qmfb_wals_sharded_create(config_.ngpus, devices.data(), int64_t(nusers()), int64_t(nitems()),
+                                            int(config_.nfactors), &sharded_));
+    QMFB_OK_OR_DIE(qmfb_wals_sharded_set_signals(sharded_, signals));
+    qmfb_signals_destroy(signals);
+    QMFB_OK_OR_DIE(qmfb_wals_sharded_set_factors(sharded_, QMFB_SIDE_ITEM, itemFactors_->getFactors().data()));
+    return;
+  }
   QMFB_OK_OR_DIE(qmfb_wals_create(config_.device, int64_t(nusers()), int64_t(nitems()), int(config_.nfactors), &dev_));
   QMFB_OK_OR_DIE(qmfb_wals_set_signals(dev_, signals));
   qmfb_signals_destroy(signals);
@@ -94,7 +107,11 @@ void WALSEngine::initTest(const std::vector<DatasetElem>& testDataset) {
 
 Double WALSEngine::iterate(int side) {
   double lossSum = 0.0;
-  QMFB_OK_OR_DIE(qmfb_wals_half_step(dev_, side, config_.confidenceWeight, config_.regularizationLambda, &lossSum));
+  if (sharded_ != nullptr) {
+    QMFB_OK_OR_DIE(qmfb_wals_sharded_half_step(sharded_, side, config_.confidenceWeight, config_.regularizationLambda, &lossSum));
+  } else {
+    QMFB_OK_OR_DIE(qmfb_wals_half_step(dev_, side, config_.confidenceWeight, config_.regularizationLambda, &lossSum));
+  }
   hostStale_ = true;
   return lossSum / nusers() / nitems();
 }
@@ -111,9 +128,14 @@ void WALSEngine::optimize() {
 }
 
 void WALSEngine::syncFactorsToHost() const {
-  if (!hostStale_ || dev_ == nullptr) return;
-  QMFB_OK_OR_DIE(qmfb_wals_get_factors(dev_, QMFB_SIDE_USER, userFactors_->getFactors().data()));
-  QMFB_OK_OR_DIE(qmfb_wals_get_factors(dev_, QMFB_SIDE_ITEM, itemFactors_->getFactors().data()));
+  if (!hostStale_ || (dev_ == nullptr && sharded_ == nullptr)) return;
+  if (sharded_ != nullptr) {
+    QMFB_OK_OR_DIE(qmfb_wals_sharded_get_factors(sharded_, QMFB_SIDE_USER, 0, userFactors_->getFactors().data()));
+    QMFB_OK_OR_DIE(qmfb_wals_sharded_get_factors(sharded_, QMFB_SIDE_ITEM, 0, itemFactors_->getFactors().data()));
+  } else {
+    QMFB_OK_OR_DIE(qmfb_wals_get_factors(dev_, QMFB_SIDE_USER, userFactors_->getFactors().data()));
+    QMFB_OK_OR_DIE(qmfb_wals_get_factors(dev_, QMFB_SIDE_ITEM, itemFactors_->getFactors().data()));
+  }
   hostStale_ = false;
 }
 
@@ -121,8 +143,12 @@ void WALSEngine::evaluate(const size_t epoch) {
   if (metricsEngine_ && !metricsEngine_->testAvgMetrics().empty() && !test_.empty() &&
       (metricsEngine_->config().alwaysCompute || epoch == config_.nepochs)) {
     LOG(INFO) << "do compute evaluate ...";
-    syncFactorsToHost();
-    computeAndRecordTestAvgMetrics(*metricsEngine_, epoch, test_, *userFactors_, *itemFactors_, nthreads_, config_.device);
+    // on the resident factors (no host round trip); with --ngpus the test users are cut over the GPUs
+    computeAndRecordTestAvgMetrics(*metricsEngine_, epoch, test_, nitems(), nthreads_,
+                                   [this](const int32_t* users, int64_t nT, const int64_t* lp, const int32_t* li, int32_t* cnt, double* ps) {
+                                     return sharded_ != nullptr ? qmfb_wals_sharded_eval_rank(sharded_, users, nT, lp, li, cnt, ps)
+                                                                : qmfb_wals_eval_rank(dev_, users, nT, lp, li, cnt, ps);
+                                   });
   }
 }
 

@@ -8,6 +8,7 @@
 #include <qmf/Engine.h>
 
 struct qmfb_wals;
+struct qmfb_wals_sharded;
 
 namespace qmf {
 
@@ -19,7 +20,8 @@ struct WALSConfig {
   Double initDistributionBound;
   std::string DistributionFile;
   int64_t seed = -1;   // additive: >= 0 seeds the initial item factors (the reference uses random_device)
-  int device = 0;      // additive: CUDA device ordinal
+  int device = 0;      // additive: CUDA device ordinal (the first one when ngpus > 1)
+  int ngpus = 1;       // additive: row-partition the half-steps over devices device .. device+ngpus-1 of this box
 };
 
 class WALSEngine : public Engine {
@@ -53,7 +55,8 @@ class WALSEngine : public Engine {
   IdIndex userIndex_, itemIndex_;
   std::unique_ptr<FactorData> userFactors_, itemFactors_;  // host mirrors
   mutable bool hostStale_ = false;
-  qmfb_wals* dev_ = nullptr;
+  qmfb_wals* dev_ = nullptr;                // ngpus == 1
+  qmfb_wals_sharded* sharded_ = nullptr;    // ngpus > 1: one process, all GPUs (qmfb_wals_sharded_*)
   TestData test_;
 };
 

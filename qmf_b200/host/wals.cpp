@@ -1,5 +1,5 @@
 // `wals` binary: same flags, defaults, log lines and file formats as the reference's
-// qmf/wals.cpp:26-107; the training loop runs on the GPU.  Additive flags: --seed, --device.
+// qmf/wals.cpp:26-107; the training loop runs on the GPU.  Additive flags: --seed, --device, --ngpus.
 #include <memory>
 
 #include <qmf/DatasetReader.h>
@@ -24,7 +24,8 @@ DEFINE_bool(test_always, false, "whether to compute test avg metrics after each 
 DEFINE_string(user_factors, "", "filename of user factors");
 DEFINE_string(item_factors, "", "filename of item factors");
 DEFINE_int64(seed, -1, "seed of the initial item factors when no distribution file is given (-1: random_device)");
-DEFINE_int32(device, 0, "CUDA device ordinal");
+DEFINE_int32(device, 0, "CUDA device ordinal (the first one when --ngpus > 1)");
+DEFINE_int32(ngpus, 1, "row-partition every half-step over this many GPUs of the box (devices device .. device+ngpus-1)");
 
 int main(int argc, char** argv) {
   qmf::flags::parse(argc, argv);
@@ -32,7 +33,8 @@ int main(int argc, char** argv) {
     LOG(WARNING) << "warning: missing model output filenames! (use options --{user,item}_factors)";
   }
   qmf::WALSConfig config{FLAGS_nepochs, FLAGS_nfactors, FLAGS_regularization_lambda, FLAGS_confidence_weight,
-                         FLAGS_init_distribution_bound, FLAGS_distribution_file, FLAGS_seed, FLAGS_device};
+                         FLAGS_init_distribution_bound, FLAGS_distribution_file, FLAGS_seed, FLAGS_device, FLAGS_ngpus};
+  CHECK_GE(FLAGS_ngpus, 1) << "--ngpus must be >= 1";
   const auto metricsEngine = std::make_unique<qmf::MetricsEngine>(
     qmf::MetricsConfig{FLAGS_num_test_users, FLAGS_test_always, FLAGS_eval_seed});
   for (const auto& metric : qmf::split(FLAGS_test_avg_metrics, ',')) {

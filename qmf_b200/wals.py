@@ -30,6 +30,20 @@ def csr_from_coo(row_id, col_id, val, col_ids_sorted=None):
     return ids, row_ptr, col_idx, np.ascontiguousarray(v)
 
 
+def _eval_rank_call(fn, handle, test_users, label_ptr, label_items):
+    """shared by the engines' eval_rank methods: (cnt, pos_scores), layout of qmfb_eval_rank"""
+    tu = np.ascontiguousarray(test_users, dtype=np.int32)
+    lp = np.ascontiguousarray(label_ptr, dtype=np.int64)
+    li = np.ascontiguousarray(label_items, dtype=np.int32)
+    nT, nl = len(tu), int(lp[-1])
+    cnt = np.zeros(nl + nT, dtype=np.int32)
+    sc = np.zeros(max(nl, 1), dtype=np.float64)
+    if li.size == 0:
+        li = np.zeros(1, np.int32)
+    check(fn(handle, tu, nT, lp, li, cnt, sc))
+    return cnt, sc[:nl]
+
+
 class Signals:
     """GPU-built dense indexing + both CSR orientations of a raw (user id, item id, value) dataset
     (qmfb_signals_*: IdIndex + WALSEngine::groupSignals on the device)."""
@@ -130,6 +144,10 @@ class WalsEngineHandle:
         check(lib.qmfb_wals_epoch_host(self._h, alpha, lam, pin, pu, pi, C.byref(loss)))
         return loss.value
 
+    def eval_rank(self, test_users, label_ptr, label_items):
+        """ranking statistics of the test users on the RESIDENT factors (qmfb_wals_eval_rank)"""
+        return _eval_rank_call(lib.qmfb_wals_eval_rank, self._h, test_users, label_ptr, label_items)
+
     def launch_count(self):
         return int(lib.qmfb_wals_launch_count(self._h))
 
@@ -203,6 +221,10 @@ class ShardedWalsHandle:
         pi = item_out.ctypes.data_as(C.c_void_p) if item_out is not None else None
         check(lib.qmfb_wals_sharded_epoch_host(self._h, alpha, lam, pin, pu, pi, C.byref(loss)))
         return loss.value
+
+    def eval_rank(self, test_users, label_ptr, label_items):
+        """the test users cut over the GPUs, each slice against that GPU's replicas (qmfb_wals_sharded_eval_rank)"""
+        return _eval_rank_call(lib.qmfb_wals_sharded_eval_rank, self._h, test_users, label_ptr, label_items)
 
     def launch_count(self):
         return int(lib.qmfb_wals_sharded_launch_count(self._h))
