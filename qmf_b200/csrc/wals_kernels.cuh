@@ -688,7 +688,10 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
   QMFB_T(tq3);
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-  if (lane == 0) bpart[warp] = csum;
+  // slot = (chunk index INSIDE the row) mod NWARPS of the chunks this warp gathered, not the warp id: which
+  // warp gathers which chunk depends on `base` (the CTA's history), the grouping of this sum must not -
+  // the loss is then bit-identical whichever CTA / GPU / shard solves the row
+  if (lane == 0) bpart[(uint32_t(warp) + SM::NWARPS - base % SM::NWARPS) % SM::NWARPS] = csum;
   QMFB_T(tq4);
   __syncthreads();  // every warp is done reading the ring before the tiles overwrite it
   QMFB_T(tq5);
@@ -734,19 +737,33 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
 // 34+ accumulator registers otherwise push the operand fragments of the trailing update into local
 // memory (3 STL.64 + 3 LDL.64 per four tiles in profiles/r01_solve_final_ncu.csv).
 // Returns false on a non-positive pivot.
-// SM is the shared-memory layout (WalsSmem<NT>: tiles in shared memory; WalsSmemBig<NT>, k > 128:
-// GT = true and the tiles live in the CTA's L2-resident global workspace `gtiles`).
-template <class SM, bool GT>
-__device__ __noinline__ bool solve_row(unsigned char* smem, double* gtiles) {
-  constexpr int NT = SM::kNT;
-  constexpr int TU = GT ? 4 : kTU;  // L2-latency tiles: keep several in flight
-  double* tiles = GT ? gtiles : reinterpret_cast<double*>(smem + SM::kOffTiles);
-  double* wt = reinterpret_cast<double*>(smem + SM::kOffW);
-  double* bcopy = reinterpret_cast<double*>(smem + SM::kOffB);
-  double* xvec = reinterpret_cast<double*>(smem + SM::kOffX);
-  double* rvec = reinterpret_cast<double*>(smem + SM::kOffR);
-  double* fscratch = reinterpret_cast<double*>(smem + SM::kOffFs);
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, tid = threadIdx.x;
+
+// Barrier of the warps that solve one row together: the whole CTA (NAMED == false, bar 0) or a group of
+// NW warps inside a warp-specialised CTA (NAMED: named barrier `bar_id`, NW * 32 threads).
+template <bool NAMED>
+__device__ __forceinline__ void group_sync(int bar_id, int nthreads) {
+  if constexpr (NAMED) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+  } else {
+    __syncthreads();
+  }
+}
+
+template <int NT>
+__host__ __device__ constexpr int tile_index(int I, int J) { return I * (NT + 1) - I * (I - 1) / 2 + (J - I); }
+
+// NW warps (warp = 0 .. NW-1, tid = 0 .. 32 NW - 1 inside the group; 32 NW >= 8 NT) solve the row whose
+// tiles are at `tiles`; wt / bcopy / xvec / rvec / fscratch are the group's scratch areas.
+template <int NT, int NW, int TU, bool NAMED>
+__device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* bcopy, double* xvec, double* rvec, double* fscratch,
+                                            int warp, int lane, int tid, int bar_id) {
+  struct SM {  // the names the body below was written against
+    static constexpr int KP = NT * 8;
+    static constexpr int NWARPS = NW;
+    static constexpr int NTILE = NT * (NT + 1) / 2 + NT;
+    __device__ static constexpr int tidx(int I, int J) { return tile_index<NT>(I, J); }
+  };
+  static_assert(NW * 32 >= NT * 8, "one thread per unknown in the back substitution");
   const int fo = tile_frag_off(lane);                        // operand-fragment offset inside a tile
   const int fw = (lane >> 2) * 8 + ((lane & 3) ^ tile_sw(lane >> 2));  // same for the transposed W tiles; k+4 half at fw ^ 4
   const int co = tile_acc_off(lane);                         // accumulator-fragment offset
@@ -765,7 +782,7 @@ __device__ __noinline__ bool solve_row(unsigned char* smem, double* gtiles) {
   QMFB_ACC(2, tp2, tp3);
   for (int I = 0; I < NT; ++I) {
     QMFB_T(ts0);
-    __syncthreads();  // W_I ready, row I of tiles final up to panel I-1
+    group_sync<NAMED>(bar_id, NW * 32);  // W_I ready, row I of tiles final up to panel I-1
     QMFB_T(ts1);
     QMFB_ACC(4, ts0, ts1);
     // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+1 .. NT
@@ -783,7 +800,7 @@ __device__ __noinline__ bool solve_row(unsigned char* smem, double* gtiles) {
     QMFB_T(ts2);
     QMFB_ACC(3, ts1, ts2);
     if (I == NT - 1) break;
-    __syncthreads();
+    group_sync<NAMED>(bar_id, NW * 32);
     QMFB_T(ts3);
     QMFB_ACC(5, ts2, ts3);
     // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT.
@@ -855,7 +872,7 @@ __device__ __noinline__ bool solve_row(unsigned char* smem, double* gtiles) {
   //      8x8 mat-vec by inv(U_JJ) and one rank-8 update of the rows above -----------------------
   //      ONE block barrier per step: the eight threads of block J live in one warp, so they exchange
   //      their finished r_J through shared memory under a __syncwarp and go straight on to x_J.
-  __syncthreads();
+  group_sync<NAMED>(bar_id, NW * 32);
   double r = 0.0;
   if (tid < SM::KP) r = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
   for (int J = NT - 1; J >= 0; --J) {
@@ -874,7 +891,7 @@ __device__ __noinline__ bool solve_row(unsigned char* smem, double* gtiles) {
       xvec[tid] = s0 + s1;
     }
     if (J == 0) break;
-    __syncthreads();  // x_J visible; also orders this step's rvec reads before the next step's writes
+    group_sync<NAMED>(bar_id, NW * 32);  // x_J visible; also orders this step's rvec reads before the next step's writes
     if (tid < 8 * J) {  // r_t -= U[t][8J .. 8J+7] . x_J
       const double* u = tiles + size_t(SM::tidx(tid >> 3, J)) * 64 + (tid & 7) * 8;
       const double* x = xvec + 8 * J;
@@ -892,6 +909,19 @@ __device__ __noinline__ bool solve_row(unsigned char* smem, double* gtiles) {
   QMFB_T(tp5);
   QMFB_ACC(8, tp4, tp5);
   return ok;
+}
+
+
+// SM is the shared-memory layout (WalsSmem<NT>: tiles in shared memory; WalsSmemBig<NT>, k > 128:
+// GT = true and the tiles live in the CTA's L2-resident global workspace `gtiles`): the whole CTA solves.
+template <class SM, bool GT>
+__device__ __forceinline__ bool solve_row(unsigned char* smem, double* gtiles) {
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  return solve_row_impl<SM::kNT, SM::NWARPS, GT ? 4 : kTU, false>(
+    GT ? gtiles : reinterpret_cast<double*>(smem + SM::kOffTiles), reinterpret_cast<double*>(smem + SM::kOffW),
+    reinterpret_cast<double*>(smem + SM::kOffB), reinterpret_cast<double*>(smem + SM::kOffX),
+    reinterpret_cast<double*>(smem + SM::kOffR), reinterpret_cast<double*>(smem + SM::kOffFs), warp, threadIdx.x & 31,
+    threadIdx.x, 0);
 }
 
 template <int NT>

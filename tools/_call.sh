@@ -1,6 +1,11 @@
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest1.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_pytest1.log
-tail -5 gpurun_out/r02_pytest1.log
-python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-bpr > gpurun_out/r02_plain1.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:wals_solve_kernel -s 2 -c 2 -o gpurun_out/r02_solve_base python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-bpr > gpurun_out/r02_ncu1.log 2>&1
-tail -3 gpurun_out/r02_plain1.log
+python -m pytest tests/test_eval_gpu.py tests/test_sharded_gpu.py tests/test_bpr_eval_gpu.py tests/test_golden_gpu.py tests/test_cli_gpu.py -x -q > gpurun_out/r02_pytest2.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_pytest2.log
+tail -30 gpurun_out/r02_pytest2.log
+python - > gpurun_out/r02_eval_bench.log 2>&1 <<'PY'
+import json, sys
+sys.path.insert(0, '.')
+import bench
+for shape in ("c2", "large"):
+    print(json.dumps(bench.run_eval_ours(shape)), flush=True)
+PY
+cat gpurun_out/r02_eval_bench.log
