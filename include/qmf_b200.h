@@ -72,13 +72,20 @@ int qmfb_gram_unpack_dev(void* stream, const double* gram_packed, int k, double*
  *   A = G + sum_s alpha r_s y_s y_s^T + lambda I,  b = sum_s (1 + alpha r_s) y_s,  x = A^{-1} b,
  *   row_loss = sum_s (1 + alpha r_s) + x^T (A - lambda I) x - 2 x^T b.
  * CSR arrays are local to the shard (row_ptr[0] == 0); X row written = row_offset + local row.
- * `order` lists local rows longest-first (any permutation is valid).  `scratch` is 2 ints
+ * `order` lists local rows longest-first (any permutation is valid).  `nnz` = row_ptr[nrows] (the host's
+ * copy; -1 if unknown): rows are bucketed by length - a half-step of short rows (mean < 1024 signals) runs
+ * the warp-specialised kernel (builder warps + two solver groups per SM), long rows two plain CTAs per SM;
+ * results do not depend on the choice.  `scratch` is 2 ints
  * (scheduler counter, error flag; the call resets both).  loss_sum (device, 1 double) receives
  * the deterministic sum of row_loss.  Asynchronous on `stream`. */
 int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset, const double* Y, int64_t ldy, int k,
                         const int64_t* row_ptr, const int32_t* col, const double* val, const int32_t* order,
-                        int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
+                        int64_t nrows, int64_t nnz, const double* gram_packed, double alpha, double lambda, double* row_loss,
                         double* loss_sum, int32_t* scratch);
+/* Process-wide choice of the row-solve kernel for k <= 128: 0 = by mean row length (default), 1 = the plain
+ * kernel (two CTAs per SM), 2 = the warp-specialised kernel.  Same results either way; for tests and
+ * measurements (environment: QMFB_SOLVE=classic|ws). */
+int qmfb_wals_set_solve_kernel(int mode);
 /* Same, with the all-gather of the solved shard FUSED into the kernel: every solved row is also
  * stored into row (row_offset + local row) of the `npeers` replicas peer_X[0..npeers) (device
  * pointers into the other ranks' factor matrices, same ldx; peer memory over NVLink, mapped with
@@ -86,7 +93,7 @@ int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset
  * follows the kernel on every rank's stream does, e.g. the allreduce of the loss). */
 int qmfb_wals_solve_peers_dev(void* stream, double* X, int64_t ldx, int64_t row_offset, const double* Y, int64_t ldy, int k,
                               const int64_t* row_ptr, const int32_t* col_idx, const double* val, const int32_t* order,
-                              int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
+                              int64_t nrows, int64_t nnz, const double* gram_packed, double alpha, double lambda, double* row_loss,
                               double* loss_sum, int32_t* scratch, double* const* peer_X, int npeers);
 /* Device buffers shareable between the ranks of one box (one process per GPU): allocate (zeroed) +
  * export a 64-byte CUDA IPC handle; map another rank's buffer; unmap; free. */
@@ -183,9 +190,12 @@ int qmfb_bpr_get_biases(qmfb_bpr_t* h, double* host);
 /* One Hogwild SGD pass over all pairs, num_neg sampled negatives each (the SGD half of one
  * iteration of BPREngine::optimize, qmf/bpr/BPREngine.cpp:151-164 -> iterate/iterateBlock ->
  * sampleRandomNegative -> update :178-220).  Negatives come from Philox4x32-10 keyed by
- * (seed, epoch); `shuffle` != 0 visits the pairs in a per-epoch pseudo-random order
- * (BPREngine::shuffle, :276-278).  *n_updates receives npairs * num_neg.  Returns
- * QMFB_ERR_NOT_FINITE if a gradient was not finite (CHECK at :184-185). */
+ * (seed, epoch); `shuffle` != 0 visits the pairs in a fresh uniformly random order (the distribution of
+ * BPREngine::shuffle's std::shuffle, :276-278; the reference shuffles AFTER an epoch, so its first epoch runs
+ * in file order: pass shuffle = 0 there), shuffle == 0 in data_ order.  Only the first
+ * hogwild_blocks * floor(npairs / hogwild_blocks) positions are visited (qmfb_bpr_set_hogwild_blocks).
+ * *n_updates receives (pairs visited) * num_neg.  Returns QMFB_ERR_NOT_FINITE if a gradient was not finite
+ * (CHECK at :184-185). */
 int qmfb_bpr_epoch(qmfb_bpr_t* h, double lr, double user_lambda, double item_lambda, double bias_lambda, int num_neg,
                    uint64_t seed, uint64_t epoch, int shuffle, int64_t* n_updates);
 /* Apply explicit triplets one after the other in the given order (BPREngine::update, :178-220);
@@ -200,6 +210,10 @@ int qmfb_bpr_eval_loss(qmfb_bpr_t* h, const int32_t* u, const int32_t* i, const 
  * --num_hogwild_threads, qmf/bpr.cpp:39): 0 = automatic, min(nusers, nitems) / 2 capped by what
  * the device can hold; more pairs in flight means staler gradients per row. */
 int qmfb_bpr_set_concurrency(qmfb_bpr_t* h, int64_t max_pairs_in_flight);
+/* --num_hogwild_threads (qmf/bpr.cpp:39): the reference cuts data_ into that many blocks of
+ * floor(ndata / numHogwildThreads) pairs and never visits the tail (BPREngine.cpp:156-160); the same
+ * tail is dropped here.  The parallelism itself is qmfb_bpr_set_concurrency's. */
+int qmfb_bpr_set_hogwild_blocks(qmfb_bpr_t* h, int64_t num_hogwild_threads);
 /* device time (ms, CUDA events on the handle's stream) of the last qmfb_bpr_epoch kernel */
 int qmfb_bpr_last_epoch_ms(qmfb_bpr_t* h, float* ms);
 double* qmfb_bpr_factors_device(qmfb_bpr_t* h, int side);

@@ -81,6 +81,9 @@ class BprEngineHandle:
     def set_concurrency(self, max_pairs_in_flight):
         check(lib.qmfb_bpr_set_concurrency(self._h, int(max_pairs_in_flight)))
 
+    def set_hogwild_blocks(self, n):
+        check(lib.qmfb_bpr_set_hogwild_blocks(self._h, int(n)))
+
     def last_epoch_ms(self):
         ms = C.c_float()
         check(lib.qmfb_bpr_last_epoch_ms(self._h, C.byref(ms)))

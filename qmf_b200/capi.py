@@ -47,10 +47,11 @@ _SIG = {
     "qmfb_gram_parts_dev": (C.c_int, [vp, vp, c_i64, c_i64, c_i64, C.c_int, C.c_int, C.c_int, vp]),
     "qmfb_gram_reduce_parts_dev": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int, vp]),
     "qmfb_gram_unpack_dev": (C.c_int, [vp, vp, C.c_int, vp]),
-    "qmfb_wals_solve_dev": (C.c_int, [vp, vp, c_i64, c_i64, vp, c_i64, C.c_int, vp, vp, vp, vp, c_i64, vp, c_f64, c_f64,
+    "qmfb_wals_solve_dev": (C.c_int, [vp, vp, c_i64, c_i64, vp, c_i64, C.c_int, vp, vp, vp, vp, c_i64, c_i64, vp, c_f64, c_f64,
                                       vp, vp, vp]),
-    "qmfb_wals_solve_peers_dev": (C.c_int, [vp, vp, c_i64, c_i64, vp, c_i64, C.c_int, vp, vp, vp, vp, c_i64, vp, c_f64,
+    "qmfb_wals_solve_peers_dev": (C.c_int, [vp, vp, c_i64, c_i64, vp, c_i64, C.c_int, vp, vp, vp, vp, c_i64, c_i64, vp, c_f64,
                                             c_f64, vp, vp, vp, C.POINTER(vp), C.c_int]),
+    "qmfb_wals_set_solve_kernel": (C.c_int, [C.c_int]),
     "qmfb_ipc_alloc": (C.c_int, [C.c_int, c_i64, C.POINTER(vp), C.c_char_p]),
     "qmfb_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(vp)]),
     "qmfb_ipc_close": (C.c_int, [vp]),
@@ -93,6 +94,7 @@ _SIG = {
     "qmfb_bpr_update_triplets": (C.c_int, [vp, p_i32, p_i32, p_i32, c_i64, c_f64, c_f64, c_f64, c_f64]),
     "qmfb_bpr_eval_loss": (C.c_int, [vp, p_i32, p_i32, p_i32, c_i64, C.POINTER(c_f64)]),
     "qmfb_bpr_set_concurrency": (C.c_int, [vp, c_i64]),
+    "qmfb_bpr_set_hogwild_blocks": (C.c_int, [vp, c_i64]),
     "qmfb_bpr_last_epoch_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "qmfb_bpr_factors_device": (vp, [vp, C.c_int]),
     "qmfb_bpr_biases_device": (vp, [vp]),

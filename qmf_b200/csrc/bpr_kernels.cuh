@@ -59,7 +59,9 @@ struct BprParams {
   double lr, user_lambda, item_lambda, bias_lambda;
   int num_neg;
   uint32_t seed_lo, seed_hi;  // Philox key: (seed, epoch)
-  uint64_t perm_mul, perm_add; // per-epoch index permutation p -> (mul * p + add) mod npairs (shuffle())
+  const int32_t* perm;        // this epoch's visiting order of the pairs (a uniformly random permutation, the
+                              // distribution std::shuffle(data_) gives, BPREngine.cpp:276-278) or nullptr = file order
+  int64_t nvisit;             // positions visited: npairs minus the tail the Hogwild block split drops (:156-160)
   int* error;             // bit 0: non-finite gradient (CHECK(std::isfinite(e)), BPREngine.cpp:184-185)
                           // bit 1: a user is positive on (almost) every item, negative sampling gave up
 };
@@ -142,8 +144,8 @@ __global__ void __launch_bounds__(256) bpr_epoch_kernel(const BprParams prm) {
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   Philox rng{prm.seed_lo, prm.seed_hi};
   bool bad = false, gave_up = false;
-  for (int64_t w = warp0; w < prm.npairs; w += nwarps) {
-    const int64_t p = int64_t((prm.perm_mul * uint64_t(w) + prm.perm_add) % uint64_t(prm.npairs));
+  for (int64_t w = warp0; w < prm.nvisit; w += nwarps) {
+    const int64_t p = prm.perm != nullptr ? int64_t(__ldg(prm.perm + w)) : w;
     const int32_t u = __ldg(prm.du + p), i = __ldg(prm.di + p);
     const int64_t lo = __ldg(prm.pos_ptr + u), hi = __ldg(prm.pos_ptr + u + 1);
     double pu[NPL], qi[NPL];
@@ -231,6 +233,19 @@ __global__ void __launch_bounds__(256) bpr_epoch_kernel(const BprParams prm) {
     if (prm.bias != nullptr && lane == 0) atomicAdd(prm.bias + i, dbi);
   }
   if (lane == 0 && (bad || gave_up)) atomicOr(prm.error, (bad ? 1 : 0) | (gave_up ? 2 : 0));
+}
+
+// sort keys of the per-epoch shuffle: key[p] = Philox(p; seed, epoch), val[p] = p.  Sorting the pairs by key
+// gives a uniformly random permutation (ties of the 32-bit keys keep index order: negligible bias).
+__global__ void bpr_shuffle_keys_kernel(uint32_t seed_lo, uint32_t seed_hi, int64_t n, uint32_t* __restrict__ key,
+                                        int32_t* __restrict__ val) {
+  Philox rng{seed_lo ^ 0x5bd1e995u, seed_hi ^ 0x27d4eb2fu};
+  for (int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; p < n; p += int64_t(gridDim.x) * blockDim.x) {
+    uint32_t r[4];
+    rng(uint32_t(p), uint32_t(uint64_t(p) >> 32), 0x9e3779b9u, 0u, r);
+    key[p] = r[0];
+    val[p] = int32_t(p);
+  }
 }
 
 // Deterministic replay: ONE warp applies the given triplets in order, writing every row back

@@ -69,6 +69,7 @@ struct EvalParams {
   const int32_t* label_items;  // per user: positive item idx, ascending
   int32_t* cnt;                // out: per user nP + 1 counters at offset label_ptr[t] + t (zeroed by the launcher)
   double* pos_scores;          // out: per user the positives' scores in ascending order (offset label_ptr[t])
+  int32_t* pos_bucket;         // per positive (label order): # positives of its user scoring strictly less
   const double* vnorm;         // ||v_x||_2 per item
   int nsplit;                  // item ranges per user group
   int* unit_counter;           // dynamic unit scheduler
@@ -83,7 +84,7 @@ __host__ __device__ inline size_t eval_smem_bytes(int kp, int stages) {
   b += size_t(kEvSpCap + kEvU) * 4;                    // bucket counters
   b += size_t(kEvU) * (8 + 8 + 4 + 4);                 // unorm, sp offset(int64), nP, user idx
   b += size_t(kEvU) * kEvI * 2;                        // re-score list (uint16)
-  b += 64;                                             // list count, unit id, flags
+  b += 64;                                             // list count, unit id, flags, slot total
   return b;
 }
 
@@ -162,6 +163,24 @@ __global__ void __launch_bounds__(256) eval_pos_kernel(const EvalParams prm) {
   }
 }
 
+// bucket of every positive ITEM (label order) among its user's sorted positives: the score kernel counts
+// positives like negatives and takes them out again at exactly this bucket.  One thread per label.
+__global__ void eval_pos_bucket_kernel(const EvalParams prm, int64_t nlabels) {
+  for (int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; q < nlabels; q += int64_t(gridDim.x) * blockDim.x) {
+    int lo = 0, hi = prm.nT;  // user t with label_ptr[t] <= q < label_ptr[t + 1]
+    while (hi - lo > 1) {
+      const int m = (lo + hi) >> 1;
+      if (prm.label_ptr[m] <= q) lo = m; else hi = m;
+    }
+    const int64_t lp0 = prm.label_ptr[lo];
+    const int nP = int(prm.label_ptr[lo + 1] - lp0);
+    const int item = prm.label_items[q];
+    const double s = eval_exact_score(prm.U + int64_t(prm.test_users[lo]) * prm.ldu, prm.V + int64_t(item) * prm.ldv,
+                                      prm.bias != nullptr ? prm.bias[item] : 0.0, prm.k);
+    prm.pos_bucket[q] = eval_lower_bound(prm.pos_scores + lp0, nP, s);
+  }
+}
+
 // ---- 2. all items by DMMA + buckets -----------------------------------------------------------------
 __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams prm) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -201,14 +220,21 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
       nPs[tid] = tid < nU ? int(prm.label_ptr[t0 + tid + 1] - lp0) : -1;
     }
     __syncthreads();
-    if (tid == 0) {
-      int off = 0;
-      for (int u = 0; u < kEvU; ++u) {
-        soff[u] = off;
-        off += max(nPs[u], 0) + 1;
+    if (warp == 0) {  // soff = exclusive prefix sum of (nP + 1) over the 64 users (two per lane)
+      const int a = max(nPs[2 * lane], 0) + 1, b = max(nPs[2 * lane + 1], 0) + 1;
+      int incl = a + b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
-      misc[2] = (off <= kEvSpCap) ? 1 : 0;
-      misc[0] = 0;
+      soff[2 * lane] = incl - a - b;
+      soff[2 * lane + 1] = incl - b;
+      if (lane == 31) {
+        misc[2] = (incl <= kEvSpCap) ? 1 : 0;
+        misc[3] = incl;
+        misc[0] = 0;
+      }
     }
     {  // U tile: 16-byte cp.async, rows of users past the end are rows of the last valid user (never bucketed)
       const int ppr = KP / 2;
@@ -222,6 +248,15 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
     }
     __syncthreads();
     const bool in_smem = misc[2] != 0;
+    const int ntot = misc[3];  // sum over the unit's users of (nP + 1)
+    auto owner = [&](int qq) {  // user u with soff[u] <= qq < soff[u + 1]
+      int lo = 0, hi = kEvU;
+      while (hi - lo > 1) {
+        const int m = (lo + hi) >> 1;
+        if (soff[m] <= qq) lo = m; else hi = m;
+      }
+      return lo;
+    };
     {  // ||u||_2 (4 threads per user), counters, sorted positives
       const int r = tid >> 2, q = tid & 3;
       double s = 0.0;
@@ -232,10 +267,11 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       if (q == 0) unorm[r] = sqrt(s);
-      if (in_smem) {
-        for (int i = tid; i < kEvSpCap + kEvU; i += kEvThreads) cnts[i] = 0;
-        for (int u = 0; u < nU; ++u) {
-          for (int i = tid; i < nPs[u]; i += kEvThreads) sps[soff[u] + i] = prm.pos_scores[lp0s[u] + i];
+      if (in_smem) {  // flattened over (user, slot): no serial loop over the 64 users
+        for (int qq = tid; qq < ntot; qq += kEvThreads) {
+          cnts[qq] = 0;
+          const int u = owner(qq), i = qq - soff[u];
+          if (i < nPs[u]) sps[qq] = prm.pos_scores[lp0s[u] + i];
         }
       }
     }
@@ -324,13 +360,20 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
           b[q] = nP;
           live[q] = (x0 + 16 * iq + 8 * nt + 2 * (lane & 3) + e) < xe;
         }
-        // four lower_bound(sp, lo) searches in lockstep (independent loads in flight)
-        for (int span = nP; span > 0; span >>= 1) {
+        if (nP <= 8) {  // a handful of positives: count them (no dependent search steps)
+          for (int m = 0; m < nP; ++m) {
+            const double v = sp[m];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (a[q] < b[q]) {
-              const int m = (a[q] + b[q]) >> 1;
-              if (sp[m] < lo[q]) a[q] = m + 1; else b[q] = m;
+            for (int q = 0; q < 4; ++q) a[q] += v < lo[q] ? 1 : 0;
+          }
+        } else {  // four lower_bound(sp, lo) searches in lockstep (independent loads in flight)
+          for (int span = nP; span > 0; span >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (a[q] < b[q]) {
+                const int m = (a[q] + b[q]) >> 1;
+                if (sp[m] < lo[q]) a[q] = m + 1; else b[q] = m;
+              }
             }
           }
         }
@@ -363,27 +406,26 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    // ---- the positive ITEMS of this item range were bucketed like negatives: take them out again ----------
-    // (a positive's own exact score is an entry of its sorted list, so its bucket is lower_bound of that score)
-    for (int ul = 0; ul < nU; ++ul) {
-      const int nP = nPs[ul];
-      const double* sp = in_smem ? sps + soff[ul] : prm.pos_scores + lp0s[ul];
-      int* cn = in_smem ? cnts + soff[ul] : prm.cnt + lp0s[ul] + (t0 + ul);
-      for (int i = tid; i < nP; i += kEvThreads) {
-        const int item = prm.label_items[lp0s[ul] + i];
-        if (item < xb || item >= xe) continue;
-        const double s = eval_exact_score(utile + size_t(ul) * LDU, prm.V + int64_t(item) * prm.ldv,
-                                          prm.bias != nullptr ? prm.bias[item] : 0.0, prm.k);
-        atomicSub(cn + eval_lower_bound(sp, nP, s), 1);
+    // ---- the positive ITEMS of this item range were bucketed like negatives: take them out again, at the
+    //      bucket eval_pos_bucket_kernel computed from their exact score; then the unit's counters go to
+    //      global memory (the item ranges of one user add up).  Flattened over (user, slot).
+    for (int qq = tid; qq < ntot; qq += kEvThreads) {
+      const int u = owner(qq), i = qq - soff[u];
+      if (i < nPs[u]) {
+        const int item = prm.label_items[lp0s[u] + i];
+        if (item >= xb && item < xe) {
+          int* cn = in_smem ? cnts + soff[u] : prm.cnt + lp0s[u] + (t0 + u);
+          atomicSub(cn + prm.pos_bucket[lp0s[u] + i], 1);
+        }
       }
     }
-    __syncthreads();
-    if (in_smem) {  // counters of this unit -> global (the item ranges of one user add up)
-      for (int ul = 0; ul < nU; ++ul) {
-        int32_t* out = prm.cnt + lp0s[ul] + (t0 + ul);
-        for (int i = tid; i <= nPs[ul]; i += kEvThreads) {
-          const int v = cnts[soff[ul] + i];
-          if (v != 0) atomicAdd(out + i, v);
+    if (in_smem) {
+      __syncthreads();
+      for (int qq = tid; qq < ntot; qq += kEvThreads) {
+        const int u = owner(qq), i = qq - soff[u];
+        if (u < nU && i <= nPs[u]) {
+          const int v = cnts[qq];
+          if (v != 0) atomicAdd(prm.cnt + lp0s[u] + (t0 + u) + i, v);
         }
       }
     }

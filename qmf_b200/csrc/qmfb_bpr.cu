@@ -2,6 +2,8 @@
 #include "qmfb_common.h"
 #include "bpr_kernels.cuh"
 
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <numeric>
 #include <vector>
@@ -14,14 +16,6 @@ __global__ void sum_partials_kernel(const double* __restrict__ v, int n, double*
     for (int i = 0; i < n; ++i) s += v[i];
     out[0] = s;
   }
-}
-static uint64_t gcd64(uint64_t a, uint64_t b) {
-  while (b) {
-    const uint64_t t = a % b;
-    a = b;
-    b = t;
-  }
-  return a;
 }
 static uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
@@ -53,6 +47,12 @@ struct qmfb_bpr {
   int64_t launches = 0;
   int sms = 148;
   int64_t max_warps = 0;  // 0 = automatic (see bpr_concurrency)
+  int64_t hogwild_blocks = 1;  // --num_hogwild_threads: only its tail-drop is mirrored (qmfb_bpr_set_hogwild_blocks)
+  // per-epoch shuffle: sort (Philox key, index) pairs
+  uint32_t *shuf_key[2] = {nullptr, nullptr};
+  int32_t *shuf_val[2] = {nullptr, nullptr};
+  void* shuf_tmp = nullptr;
+  size_t shuf_tmp_bytes = 0;
 };
 
 // Number of pairs processed concurrently (one warp each).  Every in-flight triplet computes its
@@ -84,6 +84,11 @@ static void bpr_release(qmfb_bpr* h) {
   cudaFree(h->partial);
   cudaFree(h->sum);
   cudaFree(h->trip);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(h->shuf_key[b]);
+    cudaFree(h->shuf_val[b]);
+  }
+  cudaFree(h->shuf_tmp);
   for (auto& e : h->ev) {
     if (e) cudaEventDestroy(e);
   }
@@ -219,8 +224,8 @@ static BprParams bpr_params(qmfb_bpr* h, double lr, double ul, double il, double
   p.item_lambda = il;
   p.bias_lambda = bl;
   p.error = h->error;
-  p.perm_mul = 1;
-  p.perm_add = 0;
+  p.perm = nullptr;
+  p.nvisit = h->npairs;
   return p;
 }
 
@@ -243,16 +248,30 @@ int qmfb_bpr_epoch(qmfb_bpr_t* h, double lr, double user_lambda, double item_lam
   const uint64_t key = splitmix64(seed ^ splitmix64(epoch));
   p.seed_lo = uint32_t(key);
   p.seed_hi = uint32_t(key >> 32);
-  if (shuffle && h->npairs > 2) {
-    const uint64_t n = uint64_t(h->npairs);
-    uint64_t mul = (splitmix64(key) % (n - 1)) + 1;
-    while (gcd64(mul, n) != 1) ++mul;
-    p.perm_mul = mul % n;  // npairs < 2^31 * something: mul * w fits 64 bits for npairs < 2^32
-    p.perm_add = splitmix64(key + 1) % n;
+  if (uint64_t(h->npairs) >= (1ull << 31)) return set_error(QMFB_ERR_UNSUPPORTED, "more than 2^31 training pairs");
+  if (shuffle && h->npairs > 1) {
+    // a fresh uniformly random visiting order (what std::shuffle(data_) gives the reference's next epoch)
+    const int64_t n = h->npairs;
+    if (!h->shuf_key[0]) {
+      for (int b = 0; b < 2; ++b) {
+        QMFB_CUDA(cudaMalloc(&h->shuf_key[b], size_t(n) * 4));
+        QMFB_CUDA(cudaMalloc(&h->shuf_val[b], size_t(n) * 4));
+      }
+      QMFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->shuf_tmp_bytes, h->shuf_key[0], h->shuf_key[1], h->shuf_val[0], h->shuf_val[1], n));
+      QMFB_CUDA(cudaMalloc(&h->shuf_tmp, std::max<size_t>(h->shuf_tmp_bytes, 16)));
+    }
+    bpr_shuffle_keys_kernel<<<int(std::min<int64_t>(int64_t(h->sms) * 8, (n + 255) / 256)), 256, 0, h->stream>>>(p.seed_lo, p.seed_hi, n, h->shuf_key[0],
+                                                                                                                 h->shuf_val[0]);
+    QMFB_CUDA(cudaGetLastError());
+    QMFB_CUDA(cub::DeviceRadixSort::SortPairs(h->shuf_tmp, h->shuf_tmp_bytes, h->shuf_key[0], h->shuf_key[1], h->shuf_val[0], h->shuf_val[1], n, 0, 32,
+                                              h->stream));
+    p.perm = h->shuf_val[1];
+    h->launches += 1;
   }
-  if (uint64_t(h->npairs) >= (1ull << 32)) return set_error(QMFB_ERR_UNSUPPORTED, "more than 2^32 training pairs");
+  // Hogwild dispatch of the reference: numTasks blocks of floor(ndata / numTasks) pairs, the tail is skipped
+  p.nvisit = (h->npairs / h->hogwild_blocks) * h->hogwild_blocks;
   QMFB_CUDA(cudaMemsetAsync(h->error, 0, sizeof(int32_t), h->stream));
-  const int64_t warps = std::min<int64_t>(h->npairs, bpr_concurrency(h));
+  const int64_t warps = std::max<int64_t>(1, std::min<int64_t>(p.nvisit, bpr_concurrency(h)));
   const int blocks = int((warps + 7) / 8);
   QMFB_CUDA(cudaEventRecord(h->ev[0], h->stream));
   switch ((h->k + 31) / 32) {
@@ -270,7 +289,7 @@ int qmfb_bpr_epoch(qmfb_bpr_t* h, double lr, double user_lambda, double item_lam
   h->launches += 1;
   int rc = bpr_check_error(h);
   QMFB_CUDA(cudaEventElapsedTime(&h->epoch_ms, h->ev[0], h->ev[1]));
-  if (n_updates) *n_updates = h->npairs * num_neg;
+  if (n_updates) *n_updates = p.nvisit * num_neg;
   return rc;
 }
 
@@ -349,6 +368,12 @@ int qmfb_bpr_eval_loss(qmfb_bpr_t* h, const int32_t* u, const int32_t* i, const 
 int qmfb_bpr_set_concurrency(qmfb_bpr_t* h, int64_t max_pairs_in_flight) {
   if (!h || max_pairs_in_flight < 0) return set_error(QMFB_ERR_INVALID, "qmfb_bpr_set_concurrency: bad argument");
   h->max_warps = max_pairs_in_flight;
+  return QMFB_OK;
+}
+
+int qmfb_bpr_set_hogwild_blocks(qmfb_bpr_t* h, int64_t num_hogwild_threads) {
+  if (!h || num_hogwild_threads < 0) return set_error(QMFB_ERR_INVALID, "qmfb_bpr_set_hogwild_blocks: bad argument");
+  h->hogwild_blocks = std::max<int64_t>(1, num_hogwild_threads);
   return QMFB_OK;
 }
 

@@ -150,16 +150,17 @@ int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double*
   QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   QMFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eval_score_kernel, kEvThreads, smem));
   if (occ < 1) return set_error(QMFB_ERR_UNSUPPORTED, "eval_score_kernel does not fit on an SM (nfactors %d)", k);
-  double* vnorm = nullptr;
-  QMFB_CUDA(cudaMallocAsync(&vnorm, size_t(nitems) * 8 + 16, st));
+  double* vnorm = nullptr;  // | nitems norms | unit counter | nlabels positive buckets |
+  QMFB_CUDA(cudaMallocAsync(&vnorm, size_t(nitems) * 8 + 16 + size_t(std::max<int64_t>(nlabels, 1)) * 4, st));
   int* counter = reinterpret_cast<int*>(vnorm + nitems);
+  int32_t* pos_bucket = counter + 4;
   QMFB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
   const int grid = sms * occ;
   const int64_t ngroups = (nT + kEvU - 1) / kEvU;
   int64_t nsplit = (4 * int64_t(grid) + ngroups - 1) / ngroups;
   nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, std::max<int64_t>(1, nitems / (4 * kEvI))));
-  EvalParams p{U, ldu, V, ldv, biases, k, kp, int(nitems), test_users, int(nT), label_ptr, label_items, cnt, pos_scores, vnorm,
-               int(nsplit), counter, stages, max_positives <= kEvPosSmem ? 1 : 0};
+  EvalParams p{U, ldu, V, ldv, biases, k, kp, int(nitems), test_users, int(nT), label_ptr, label_items, cnt, pos_scores, pos_bucket,
+               vnorm, int(nsplit), counter, stages, max_positives <= kEvPosSmem ? 1 : 0};
   eval_item_norm_kernel<<<std::min<int64_t>(int64_t(sms) * 8, (nitems + 7) / 8), 256, 0, st>>>(V, ldv, k, int(nitems), vnorm);
   eval_pos_kernel<<<int(std::min<int64_t>(nT, int64_t(sms) * 8)), 256, 0, st>>>(p);
   cudaError_t e = cudaGetLastError();
@@ -180,6 +181,10 @@ int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double*
     if (e == cudaSuccess) e = cudaMemcpyAsync(pos_scores, sorted, size_t(nlabels) * 8, cudaMemcpyDeviceToDevice, st);
     if (sorted) cudaFreeAsync(sorted, st);
     if (tmp) cudaFreeAsync(tmp, st);
+  }
+  if (e == cudaSuccess && nlabels > 0) {
+    eval_pos_bucket_kernel<<<int(std::min<int64_t>(int64_t(sms) * 8, (nlabels + 255) / 256)), 256, 0, st>>>(p, nlabels);
+    e = cudaGetLastError();
   }
   if (e == cudaSuccess) {
     eval_score_kernel<<<grid, kEvThreads, smem, st>>>(p);

@@ -4,6 +4,7 @@
 #include "wals_big.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 #include <numeric>
@@ -74,8 +75,20 @@ static int keep_pool_cached() {
   });
 }
 
+// 0 = automatic (by mean row length), 1 = always the plain kernel, 2 = always the warp-specialised kernel (k <= 128)
+static std::atomic<int> g_solve_kernel{[] {
+  const char* e = getenv("QMFB_SOLVE");
+  return e == nullptr ? 0 : (e[0] == 'c' ? 1 : (e[0] == 'w' ? 2 : 0));
+}()};
+
+// rows of the matrix the next solve gathers from (set by the engines right before the launch; 0 = unknown)
+static std::atomic<int64_t> g_gather_rows_hint{0};
+
+constexpr int kWsMaxMeanRow = 1024;  // mean signals per row below which a half-step counts as "short rows"
+
+// nnz_hint: number of signals of the rows being solved (-1: unknown)
 template <int NT>
-static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_sum, int32_t* scratch) {
+static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_sum, int32_t* scratch, int64_t nnz_hint) {
   if (int rc = keep_pool_cached()) return rc;
   using SM = WalsSmem<NT>;
   static PerDeviceCfg cfg;
@@ -105,7 +118,34 @@ static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_su
     SolveParams run = prm;
     static const bool no_long = getenv("QMFB_NO_LONG_ROWS") != nullptr;  // measurement switch: ignore the sums
     run.long_sum = no_long ? nullptr : lp.sum;
-    wals_solve_kernel<NT><<<grid, SM::NTHREADS, SM::kBytes, st>>>(run);
+    // Row bucketing by length (north_star): half-steps of SHORT rows (solve-latency bound: the Cholesky chain of
+    // a row is longer than its build) run the warp-specialised kernel - one CTA per SM, builders + two solver
+    // groups, three rows in flight; LONG rows (build bound) run two plain CTAs per SM.
+    // qmfb_wals_set_solve_kernel / QMFB_SOLVE=classic|ws override the choice (tests, measurements).
+    bool ws = NT == 16 && nnz_hint >= 0 && nnz_hint < int64_t(kWsMaxMeanRow) * prm.nrows;
+    const int mode = g_solve_kernel.load();
+    if (mode == 1) ws = false;
+    if (mode == 2) ws = true;
+    if (ws) {
+      using WS = WalsSmemWs<NT>;
+      static PerDeviceCfg wcfg;
+      int wcap = 0;
+      if (int rc = per_device(wcfg, &wcap, [](int dev, int* cap) -> int {
+            QMFB_CUDA(cudaFuncSetAttribute(wals_solve_ws_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WS::kBytes)));
+            int sms = 0, occ = 0;
+            QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            QMFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wals_solve_ws_kernel<NT>, WS::NTHREADS, WS::kBytes));
+            if (occ < 1) return set_error(QMFB_ERR_CUDA, "wals_solve_ws_kernel does not fit on an SM");
+            *cap = sms * occ;
+            return QMFB_OK;
+          })) {
+        cudaFreeAsync(long_buf, st);
+        return rc;
+      }
+      wals_solve_ws_kernel<NT><<<int(std::min<int64_t>(wcap, prm.nrows)), WS::NTHREADS, WS::kBytes, st>>>(run);
+    } else {
+      wals_solve_kernel<NT><<<grid, SM::NTHREADS, SM::kBytes, st>>>(run);
+    }
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(long_buf, st);
     QMFB_CUDA(e);
@@ -184,6 +224,12 @@ int qmfb_debug_set_flags(int flags) {
   return QMFB_OK;
 }
 #endif
+
+int qmfb_wals_set_solve_kernel(int mode) {
+  if (mode < 0 || mode > 2) return set_error(QMFB_ERR_INVALID, "qmfb_wals_set_solve_kernel: mode must be 0 (auto), 1 (plain) or 2 (warp-specialised)");
+  g_solve_kernel.store(mode);
+  return QMFB_OK;
+}
 
 int qmfb_padded_k(int k) {
   if (k < 1 || k > 256) return set_error(QMFB_ERR_UNSUPPORTED, "nfactors must be in [1, 256] (got %d)", k);
@@ -283,15 +329,15 @@ int qmfb_gram_unpack_dev(void* stream, const double* gram_packed, int k, double*
 
 int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset, const double* Y, int64_t ldy, int k,
                         const int64_t* row_ptr, const int32_t* col, const double* val, const int32_t* order,
-                        int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
+                        int64_t nrows, int64_t nnz, const double* gram_packed, double alpha, double lambda, double* row_loss,
                         double* loss_sum, int32_t* scratch) {
-  return qmfb_wals_solve_peers_dev(stream, X, ldx, row_offset, Y, ldy, k, row_ptr, col, val, order, nrows, gram_packed, alpha,
+  return qmfb_wals_solve_peers_dev(stream, X, ldx, row_offset, Y, ldy, k, row_ptr, col, val, order, nrows, nnz, gram_packed, alpha,
                                    lambda, row_loss, loss_sum, scratch, nullptr, 0);
 }
 
 int qmfb_wals_solve_peers_dev(void* stream, double* X, int64_t ldx, int64_t row_offset, const double* Y, int64_t ldy, int k,
                               const int64_t* row_ptr, const int32_t* col, const double* val, const int32_t* order,
-                              int64_t nrows, const double* gram_packed, double alpha, double lambda, double* row_loss,
+                              int64_t nrows, int64_t nnz_hint, const double* gram_packed, double alpha, double lambda, double* row_loss,
                               double* loss_sum, int32_t* scratch, double* const* peer_X, int npeers) {
   const int kp = qmfb_padded_k(k);
   if (kp < 0) return kp;
@@ -304,17 +350,28 @@ int qmfb_wals_solve_peers_dev(void* stream, double* X, int64_t ldx, int64_t row_
     return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_dev: Y must be 16-byte aligned with an even row stride");
   }
   SolveParams prm{X, ldx, row_offset, Y, ldy, k, row_ptr, col, val, order, int(nrows), gram_packed, alpha, lambda,
-                  row_loss, scratch + 1, npeers, {}, nullptr};
+                  row_loss, scratch + 1, npeers, {}, nullptr, 0};
+  {
+    // TMA gathers only when the gathered matrix is comfortably L2 resident (see SolveParams::tma_gather);
+    // the launcher does not know the row count of Y: the largest column index bounds it from the CSR's side,
+    // the caller's hint (ncols_hint) from the engine's.  QMFB_TMA_GATHER=0|1 overrides (measurements).
+    static const char* e = getenv("QMFB_TMA_GATHER");
+    if (e != nullptr) {
+      prm.tma_gather = e[0] == '1';
+    } else {
+      prm.tma_gather = g_gather_rows_hint.load() > 0 && g_gather_rows_hint.load() * int64_t(kp) * 8 <= (int64_t(48) << 20);
+    }
+  }
   for (int p = 0; p < npeers; ++p) {
     if (!peer_X[p]) return set_error(QMFB_ERR_INVALID, "qmfb_wals_solve_peers_dev: null peer pointer %d", p);
     prm.peerX[p] = peer_X[p];
   }
   auto st = static_cast<cudaStream_t>(stream);
   switch (kp / 8) {
-    case 4: return launch_solve<4>(st, prm, loss_sum, scratch);
-    case 8: return launch_solve<8>(st, prm, loss_sum, scratch);
-    case 12: return launch_solve<12>(st, prm, loss_sum, scratch);
-    case 16: return launch_solve<16>(st, prm, loss_sum, scratch);
+    case 4: return launch_solve<4>(st, prm, loss_sum, scratch, nnz_hint);
+    case 8: return launch_solve<8>(st, prm, loss_sum, scratch, nnz_hint);
+    case 12: return launch_solve<12>(st, prm, loss_sum, scratch, nnz_hint);
+    case 16: return launch_solve<16>(st, prm, loss_sum, scratch, nnz_hint);
     case 20: return launch_solve_big<20>(st, prm, loss_sum, scratch);
     case 24: return launch_solve_big<24>(st, prm, loss_sum, scratch);
     case 28: return launch_solve_big<28>(st, prm, loss_sum, scratch);
@@ -537,7 +594,7 @@ static int wals_half_step_async(qmfb_wals* h, int side, double alpha, double lam
   if (rc) return rc;
   QMFB_CUDA(cudaEventRecord(h->ev[1], h->stream));
   rc = qmfb_wals_solve_dev(h->stream, h->F[side], h->kp, h->row_begin[side], h->F[other], h->kp, h->k, h->row_ptr[side],
-                           h->col[side], h->val[side], h->order[side], h->nrows[side], h->gram_packed, alpha, lambda,
+                           h->col[side], h->val[side], h->order[side], h->nrows[side], h->nnz[side], h->gram_packed, alpha, lambda,
                            h->row_loss, h->loss_sum, h->scratch);
   if (rc) return rc;
   QMFB_CUDA(cudaEventRecord(h->ev[2], h->stream));

@@ -170,7 +170,7 @@ int half_step_async(qmfb_wals_sharded* h, int side, double alpha, double lambda,
       if (e != d) peers[np++] = h->sh[size_t(e)].F[side];
     }
     if (int rc = qmfb_wals_solve_peers_dev(s.stream, s.F[side], h->kp, s.row_begin[side], s.F[other], h->kp, h->k, s.row_ptr[side],
-                                           s.col[side], s.val[side], s.order[side], s.nrows[side], s.gram_packed, alpha, lambda,
+                                           s.col[side], s.val[side], s.order[side], s.nrows[side], s.nnz[side], s.gram_packed, alpha, lambda,
                                            s.row_loss, s.loss_sum, s.scratch, peers, np)) return rc;
     if (d == 0) QMFB_CUDA(cudaEventRecord(h->tev[2], s.stream));
     h->launches += 2 + ((s.nrows[side] > 0) ? (h->kp <= 128 ? 3 : 1) : 0);  // reduce, sum, [long partial, long reduce,] solve

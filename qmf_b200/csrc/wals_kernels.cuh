@@ -126,6 +126,9 @@ struct WalsSmem {
   static constexpr int NTHREADS = NWARPS * 32;  // == 2 * KP
   static constexpr int NTILE_A = NT * (NT + 1) / 2;
   static constexpr int NTILE = NTILE_A + NT;    // + one tile column for b
+  static constexpr int kRing = kStages;         // ring depth of the gather pipeline
+  static constexpr int kAhead = kStages - 2;    // chunks in flight beyond the one being consumed: the stage refilled
+                                                // was consumed TWO chunks ago (nobody waits for the slowest warp)
   static constexpr size_t kStageBytes = size_t(kStages) * kChunk * LD * 8;
   static constexpr size_t kTileBytes = size_t(NTILE) * 64 * 8;
   static constexpr size_t kMainBytes = kStageBytes > kTileBytes ? kStageBytes : kTileBytes;
@@ -148,6 +151,49 @@ struct WalsSmem {
   __host__ __device__ static constexpr int gidx(int I, int J) { return I * NT - I * (I - 1) / 2 + (J - I); }
 };
 
+// Layout of the WARP-SPECIALISED solve kernel (wals_solve_ws_kernel): one CTA per SM made of
+//   NT/2 builder warps  - gather + DMMA build of row r into registers, then into tile buffer r % 2
+//   2 groups of NT/4 solver warps - group g runs the Cholesky / back substitution / loss / store of the
+//                         rows r = g (mod 2) out of tile buffer g while the builders are already on the
+//                         next rows
+// Nothing aliases: gather ring | 2 tile buffers | per-group solve scratch.  Three rows are in flight per
+// SM (one building, two solving) instead of two, and the DMMA pipe is never idle because a CTA is in its
+// latency-bound solve phase.
+#ifndef QMFB_WS_RING
+#define QMFB_WS_RING 3
+#endif
+template <int NT>
+struct WalsSmemWs {
+  static constexpr int kNT = NT;
+  static constexpr int KP = NT * 8;
+  static constexpr int LD = KP + 4;
+  static constexpr int NWARPS = NT / 2;                 // builder warps (same warp roles as WalsSmem)
+  static constexpr int NSOLVE = NT / 4;                 // warps per solver group: 32 * NSOLVE == KP threads
+  static constexpr int NTHREADS = 32 * (NWARPS + 2 * NSOLVE);
+  static constexpr int NTILE_A = NT * (NT + 1) / 2;
+  static constexpr int NTILE = NTILE_A + NT;
+  static constexpr int kRing = QMFB_WS_RING;
+  static constexpr int kAhead = kRing - 1;      // one builder group per SM: deeper prefetch, the refilled stage was
+                                                // consumed in the previous chunk (the gathering warp may wait briefly)
+  static constexpr size_t kStageBytes = size_t(kRing) * kChunk * LD * 8;
+  static constexpr size_t kTileBytes = size_t(NTILE) * 64 * 8;
+  static constexpr size_t kOffStage = 0;
+  static constexpr size_t kOffTiles = kStageBytes;                               // 2 buffers
+  static constexpr size_t kOffWts = kOffTiles + 2 * kTileBytes;                  // kRing * 2 * kChunk doubles
+  static constexpr size_t kOffW = kOffWts + size_t(kRing) * 2 * kChunk * 8;      // 2 groups x NT inverse diagonal tiles
+  static constexpr size_t kOffB = kOffW + 2 * size_t(NT) * 64 * 8;               // 2 x b copy (KP)
+  static constexpr size_t kOffX = kOffB + 2 * size_t(KP) * 8;                    // 2 x x (KP)
+  static constexpr size_t kOffR = kOffX + 2 * size_t(KP) * 8;                    // 2 x back-substitution rhs (8)
+  static constexpr size_t kOffFs = kOffR + 2 * 64;                               // 2 x pivot-row scratch (16 doubles)
+  static constexpr size_t kOffBh = kOffFs + 2 * 128;                             // 2 x partial sums of (1 + alpha r) (8)
+  static constexpr size_t kOffBar = kOffBh + 2 * 64;                             // full[kRing], empty[kRing], tfull[2], tempty[2]
+  static constexpr size_t kOffRow = kOffBar + ((size_t(2 * kRing + 4) * 8 + 15) / 16) * 16;  // 2 row slots x 32 bytes
+  static constexpr size_t kBytes = kOffRow + 64;
+  static_assert(NT % 4 == 0, "NT must be a multiple of 4");
+  __host__ __device__ static constexpr int tidx(int I, int J) { return I * (NT + 1) - I * (I - 1) / 2 + (J - I); }
+  __host__ __device__ static constexpr int gidx(int I, int J) { return I * NT - I * (I - 1) / 2 + (J - I); }
+};
+
 // ------------------------------------------------------------------------------------------
 // DMMA inner loop of one staged chunk for warp role W (each warp owns NT+1 of the upper tiles).
 // This is the only code that differs between warps; everything else is a single copy.
@@ -158,9 +204,8 @@ struct WalsSmem {
 // column tiles of tile rows I0 / I1,  b(8I+m) = sum_s y_s(8I+m) * wb_s, i.e. the operand fragment
 // already in registers times a B fragment that holds wb_s in column 0 and zeros elsewhere - exactly
 // the (column 0 = b) tile the blocked Cholesky carries as column NT.
-template <int NT, int W, bool WITH_B>
+template <int NT, int W, bool WITH_B, class SM = WalsSmem<NT>>
 __device__ __forceinline__ void chunk_mma_rows(double (&acc)[NT + 3][2], const double* sb, const double* wt, int lane) {
-  using SM = WalsSmem<NT>;
   constexpr int I0 = W, I1 = NT - 1 - W, N0 = NT - I0, N1 = NT - I1, D = I1 - I0;
 #pragma unroll
   for (int s0 = 0; s0 < kChunk; s0 += 4) {
@@ -185,14 +230,14 @@ __device__ __forceinline__ void chunk_mma_rows(double (&acc)[NT + 3][2], const d
   }
 }
 
-template <int NT, int W, bool WITH_B>
+template <int NT, int W, bool WITH_B, class SM = WalsSmem<NT>>
 __device__ __forceinline__ void chunk_mma_dispatch(int warp, double (&acc)[NT + 3][2], const double* sb,
                                                    const double* wt, int lane) {
   if constexpr (W < NT / 2) {
     if (warp == W) {
-      chunk_mma_rows<NT, W, WITH_B>(acc, sb, wt, lane);
+      chunk_mma_rows<NT, W, WITH_B, SM>(acc, sb, wt, lane);
     } else {
-      chunk_mma_dispatch<NT, W + 1, WITH_B>(warp, acc, sb, wt, lane);
+      chunk_mma_dispatch<NT, W + 1, WITH_B, SM>(warp, acc, sb, wt, lane);
     }
   }
 }
@@ -480,6 +525,11 @@ struct SolveParams {
   int npeers;
   double* peerX[kMaxPeers];
   const double* long_sum;  // [kLongMax][LongRow<NT>::kLen] prebuilt sums of the extremely long rows, or nullptr
+  // 1: gather the factor rows with TMA bulk copies (one 8 KP-byte cp.async.bulk per row, issued by 16 lanes)
+  // instead of 16-byte cp.async (32 per lane and chunk).  Cheap to issue, but the TMA engine's outstanding-request
+  // window starves the loop when the gathered matrix is DRAM resident (profiles/r01_solve_v1_*): the launcher
+  // sets it only when Y fits the L2 comfortably (user half-step of C4: 18 MB of item factors).
+  int tma_gather;
 };
 
 // Store the solved row (KP doubles in shared memory) to X and to every peer replica.  Target t is
@@ -559,9 +609,11 @@ __device__ unsigned long long g_phase_cycles[24];
 __device__ int g_debug_flags;  // bit 0: skip the trailing updates of the non-diagonal warps (timing experiments only)
 #define QMFB_T(var) const long long var = clock64()
 #define QMFB_ACC(idx, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[idx], (unsigned long long)((b) - (a))); } while (0)
+#define QMFB_ACC_IF(cond, idx, a, b) do { if (cond) atomicAdd(&g_phase_cycles[idx], (unsigned long long)((b) - (a))); } while (0)
 #else
 #define QMFB_T(var)
 #define QMFB_ACC(idx, a, b)
+#define QMFB_ACC_IF(cond, idx, a, b)
 #endif
 
 // Build phase of one row.  The kernel keeps its per-row schedule state in shared memory, so only
@@ -577,24 +629,28 @@ __device__ int g_debug_flags;  // bit 0: skip the trailing updates of the non-di
 // 1/NWARPS of the bookkeeping of every chunk (the first version) all warps left the DMMA pipe at
 // the same time each chunk: measured 885 + 782 cycles of bookkeeping per chunk and warp around
 // 1 088 cycles' worth of DMMA issue, tensor pipe 69 % busy (tools/exp_phases.py).
-template <int NT>
+// WS (warp-specialised kernel): the tiles go to `tiles` (a buffer the solver group of row r - 2 may still be
+// reading: wait for `tempty` first when `tempty_wait`), nothing aliases the ring and only the builder warps
+// call this.  !WS: the tiles alias the ring, the whole CTA calls this.
+template <class SM, bool WS>
 __device__ __forceinline__ void build_row(unsigned char* smem, const double* __restrict__ Y, int64_t ldy,
                                           const int32_t* __restrict__ col, const double* __restrict__ val,
                                           const double* __restrict__ gram, double alpha, double lambda, int k,
-                                          int64_t p0, int64_t p1, uint32_t base, const double* __restrict__ lsrc) {
+                                          int64_t p0, int64_t p1, uint32_t base, const double* __restrict__ lsrc,
+                                          double* tiles, double* bpart, uint64_t* tempty, uint32_t tempty_parity,
+                                          bool tempty_wait, bool tma_gather) {
   // lsrc != nullptr: an extremely long row whose sum over its entries was built ahead by
   // long_row_partial_kernel (then p1 == p0 here: no gather loop, start from Gram + that sum)
-  using SM = WalsSmem<NT>;
+  constexpr int NT = SM::kNT;
+  constexpr int kStages = SM::kRing;  // (shadows the global ring depth: this layout's)
   double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
-  double* tiles = reinterpret_cast<double*>(smem + SM::kOffTiles);
   double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
-  double* bpart = reinterpret_cast<double*>(smem + SM::kOffBh);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
   uint64_t* empty = full + kStages;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   constexpr int PPR = SM::KP / 2;             // 16-byte pieces per gathered row
   constexpr int NCOPY = kChunk * PPR / 32;    // cp.async per lane per chunk
-  constexpr int kAhead = kStages - 2;         // chunks in flight beyond the one being consumed
+  constexpr int kAhead = SM::kAhead;          // chunks in flight beyond the one being consumed
   QMFB_T(tq0);
   const int nch = int((p1 - p0 + kChunk - 1) / kChunk);
   const uint32_t lim = base + uint32_t(nch);  // the ring is reused as tile storage: no cross-row prefetch
@@ -621,13 +677,26 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
       csum += wb;
       mbar_arrive(&full[st]);
     }
+    if (tma_gather) {
+      // same 32 + kChunk arrivals as the cp.async form; lane 0's carries the byte count of the chunk
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[st], uint32_t(kChunk) * SM::KP * 8);
+      } else {
+        mbar_arrive(&full[st]);
+      }
+      __syncwarp();
+      if (lane < kChunk) {
+        bulk_g2s(stagebuf + (size_t(st) * kChunk + lane) * SM::LD, Y + int64_t(pcol) * ldy, SM::KP * 8, &full[st]);
+      }
+    } else {
 #pragma unroll 8
-    for (int m = 0; m < NCOPY; ++m) {
-      const int q = lane + 32 * m, row = q / PPR, piece = q % PPR;
-      const int32_t c = __shfl_sync(0xffffffffu, pcol, row);
-      cp_async16(stagebuf + (size_t(st) * kChunk + row) * SM::LD + piece * 2, Y + int64_t(c) * ldy + piece * 2);
+      for (int m = 0; m < NCOPY; ++m) {
+        const int q = lane + 32 * m, row = q / PPR, piece = q % PPR;
+        const int32_t c = __shfl_sync(0xffffffffu, pcol, row);
+        cp_async16(stagebuf + (size_t(st) * kChunk + row) * SM::LD + piece * 2, Y + int64_t(c) * ldy + piece * 2);
+      }
+      cp_async_arrive(&full[st]);
     }
-    cp_async_arrive(&full[st]);
     mine += SM::NWARPS;
     prefetch_idx();
   };
@@ -657,7 +726,7 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
 #endif
   for (int c = 0; c < nch; ++c) {
     const uint32_t gc = base + c, st = gc % kStages;
-    // the stage refilled here was consumed TWO chunks ago: its empty barrier completed long ago
+    // (classic layout: the stage refilled here was consumed TWO chunks ago, its empty barrier completed long ago)
     QMFB_T(tb0);
     if (mine == gc + kAhead && mine < lim) issue_mine();
     QMFB_T(tb1);
@@ -673,9 +742,9 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
 #pragma unroll
       for (int j = 0; j < kChunk / 2; ++j) bacc = fma(pw[2 * j], pb[2 * j * SM::LD], bacc);
     }
-    chunk_mma_dispatch<NT, 0, false>(warp, acc, sb, w8, lane);
+    chunk_mma_dispatch<NT, 0, false, SM>(warp, acc, sb, w8, lane);
 #else
-    chunk_mma_dispatch<NT, 0, true>(warp, acc, sb, w8, lane);
+    chunk_mma_dispatch<NT, 0, true, SM>(warp, acc, sb, w8, lane);
 #endif
     QMFB_T(tb3);
     __syncwarp();
@@ -688,13 +757,17 @@ __device__ __forceinline__ void build_row(unsigned char* smem, const double* __r
   QMFB_T(tq3);
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+  QMFB_T(tq4);
+  if constexpr (WS) {
+    if (tempty_wait) mbar_wait(tempty, tempty_parity);  // the solver group is done with this buffer (row r - 2)
+  } else {
+    __syncthreads();  // every warp is done reading the ring before the tiles overwrite it
+  }
+  QMFB_T(tq5);
   // slot = (chunk index INSIDE the row) mod NWARPS of the chunks this warp gathered, not the warp id: which
   // warp gathers which chunk depends on `base` (the CTA's history), the grouping of this sum must not -
   // the loss is then bit-identical whichever CTA / GPU / shard solves the row
   if (lane == 0) bpart[(uint32_t(warp) + SM::NWARPS - base % SM::NWARPS) % SM::NWARPS] = csum;
-  QMFB_T(tq4);
-  __syncthreads();  // every warp is done reading the ring before the tiles overwrite it
-  QMFB_T(tq5);
   // tiles to shared memory: A(i,i) += lambda (WALSEngine.cpp:290-292), unit pivot on padding
   const int r = lane >> 2, c0 = 2 * (lane & 3);
 #pragma unroll
@@ -752,17 +825,20 @@ __device__ __forceinline__ void group_sync(int bar_id, int nthreads) {
 template <int NT>
 __host__ __device__ constexpr int tile_index(int I, int J) { return I * (NT + 1) - I * (I - 1) / 2 + (J - I); }
 
+template <int NT, int NW>
+struct SolveDims {  // the names the body of solve_row_impl was written against
+  static constexpr int KP = NT * 8;
+  static constexpr int NWARPS = NW;
+  static constexpr int NTILE = NT * (NT + 1) / 2 + NT;
+  __host__ __device__ static constexpr int tidx(int I, int J) { return tile_index<NT>(I, J); }
+};
+
 // NW warps (warp = 0 .. NW-1, tid = 0 .. 32 NW - 1 inside the group; 32 NW >= 8 NT) solve the row whose
 // tiles are at `tiles`; wt / bcopy / xvec / rvec / fscratch are the group's scratch areas.
 template <int NT, int NW, int TU, bool NAMED>
 __device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* bcopy, double* xvec, double* rvec, double* fscratch,
                                             int warp, int lane, int tid, int bar_id) {
-  struct SM {  // the names the body below was written against
-    static constexpr int KP = NT * 8;
-    static constexpr int NWARPS = NW;
-    static constexpr int NTILE = NT * (NT + 1) / 2 + NT;
-    __device__ static constexpr int tidx(int I, int J) { return tile_index<NT>(I, J); }
-  };
+  using SM = SolveDims<NT, NW>;
   static_assert(NW * 32 >= NT * 8, "one thread per unknown in the back substitution");
   const int fo = tile_frag_off(lane);                        // operand-fragment offset inside a tile
   const int fw = (lane >> 2) * 8 + ((lane & 3) ^ tile_sw(lane >> 2));  // same for the transposed W tiles; k+4 half at fw ^ 4
@@ -773,18 +849,18 @@ __device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* b
   // ---- blocked Cholesky, panel width 8; forward substitution rides along in column NT ------
   bool ok = true;
   QMFB_T(tp2);
-  QMFB_ACC(1, tp1, tp2);
+  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 1, tp1, tp2);
   if (warp == 0) {
     const double2 a = *reinterpret_cast<const double2*>(tiles + size_t(SM::tidx(0, 0)) * 64 + co);
     ok = factor_diag_tile(a.x, a.y, wt, fscratch, lane);
   }
   QMFB_T(tp3);
-  QMFB_ACC(2, tp2, tp3);
+  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 2, tp2, tp3);
   for (int I = 0; I < NT; ++I) {
     QMFB_T(ts0);
     group_sync<NAMED>(bar_id, NW * 32);  // W_I ready, row I of tiles final up to panel I-1
     QMFB_T(ts1);
-    QMFB_ACC(4, ts0, ts1);
+    QMFB_ACC_IF(tid == 0 && bar_id <= 1, 4, ts0, ts1);
     // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+1 .. NT
     {
       const double w0 = wt[I * 64 + fw], w1 = wt[I * 64 + (fw ^ 4)];
@@ -798,11 +874,11 @@ __device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* b
       }
     }
     QMFB_T(ts2);
-    QMFB_ACC(3, ts1, ts2);
+    QMFB_ACC_IF(tid == 0 && bar_id <= 1, 3, ts1, ts2);
     if (I == NT - 1) break;
     group_sync<NAMED>(bar_id, NW * 32);
     QMFB_T(ts3);
-    QMFB_ACC(5, ts2, ts3);
+    QMFB_ACC_IF(tid == 0 && bar_id <= 1, 5, ts2, ts3);
     // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT.
     //     One warp updates the next diagonal tile first and factors it right away (look-ahead)
     //     while the other warps sweep the rest (kTU tiles in flight each).
@@ -822,8 +898,8 @@ __device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* b
       QMFB_T(tf0);  // the updated tile goes to the factor in registers (same fragment layout); U_II itself is never read again
       ok = factor_diag_tile(c[0], c[1], wt + (I + 1) * 64, fscratch, lane) && ok;
       QMFB_T(tf1);
-      QMFB_ACC(2, tf0, tf1);
-      QMFB_ACC(6, ts3, tf0);
+      QMFB_ACC_IF(tid == 0 && bar_id <= 1, 2, tf0, tf1);
+      QMFB_ACC_IF(tid == 0 && bar_id <= 1, 6, ts3, tf0);
     }
 #ifdef QMFB_PROFILE_PHASES
     if ((g_debug_flags & 1) == 0)
@@ -866,7 +942,7 @@ __device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* b
     }
   }
   QMFB_T(tp4);
-  QMFB_ACC(7, tp3, tp4);
+  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 7, tp3, tp4);
 
   // ---- back substitution U x = z: thread t < KP keeps r_t in a register; per block step one
   //      8x8 mat-vec by inv(U_JJ) and one rank-8 update of the rows above -----------------------
@@ -907,7 +983,7 @@ __device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* b
     }
   }
   QMFB_T(tp5);
-  QMFB_ACC(8, tp4, tp5);
+  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 8, tp4, tp5);
   return ok;
 }
 
@@ -986,8 +1062,9 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
     const int opos = slot_of(it);
     const bool is_long = prm.long_sum != nullptr && opos < kLongMax && (cs->p1 - cs->p0) >= kLongRow;
     const int64_t bp1 = is_long ? cs->p0 : cs->p1;
-    build_row<NT>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k, cs->p0, bp1, cs->base,
-                  is_long ? prm.long_sum + size_t(opos) * LongRow<NT>::kLen : nullptr);
+    build_row<SM, false>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k, cs->p0, bp1, cs->base,
+                         is_long ? prm.long_sum + size_t(opos) * LongRow<NT>::kLen : nullptr, tiles, bhalf, nullptr, 0u, false,
+                         prm.tma_gather != 0);
     QMFB_T(tp1);
     QMFB_ACC(0, tp0, tp1);
     int64_t np0 = 0, np1 = 0;
@@ -1036,6 +1113,138 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
   }
   // peer replicas: make this thread's NVLink stores visible system-wide before it retires (kernel
   // completion implies it; stated explicitly because other ranks read the rows right after the next collective)
+  if (prm.npeers > 0) __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------
+// warp-specialised variant (see WalsSmemWs): builders and two solver groups in one CTA per SM
+// ------------------------------------------------------------------------------------------
+#ifndef QMFB_WS_TU
+#define QMFB_WS_TU 2   // trailing-update tiles in flight per solver warp (3 sweep warps instead of 7)
+#endif
+
+template <int NT>
+__global__ void __launch_bounds__(WalsSmemWs<NT>::NTHREADS, 1) wals_solve_ws_kernel(const SolveParams prm) {
+  using SM = WalsSmemWs<NT>;
+  constexpr int NB = SM::NWARPS, NS = SM::NSOLVE;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
+  uint64_t* empty = full + SM::kRing;
+  uint64_t* tfull = empty + SM::kRing;   // [2] tiles of buffer b are complete (builders -> solver group b)
+  uint64_t* tempty = tfull + 2;          // [2] solver group b is done with buffer b
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < SM::kRing; ++s) {
+      mbar_init(&full[s], 32 + kChunk);
+      mbar_init(&empty[s], NB);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], NB * 32);
+      mbar_init(&tempty[b], NS * 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int G = gridDim.x, bid = blockIdx.x;
+  auto slot_of = [&](int i) { return i * G + ((i & 1) ? (G - 1 - bid) : bid); };
+
+  if (warp < NB) {
+    // ================= builders: rows it = 0, 1, 2, ... of this CTA's serpentine schedule =================
+    struct RowSlot {
+      int64_t p0, p1;
+      int32_t row;
+      uint32_t base;
+      int64_t pad;
+    };
+    volatile RowSlot* slots = reinterpret_cast<volatile RowSlot*>(smem + SM::kOffRow);
+    if (tid == 0) {
+      const int s0 = slot_of(0);
+      const int r0 = s0 < prm.nrows ? prm.order[s0] : -1;
+      slots[0].row = r0;
+      slots[0].base = 0u;
+      slots[0].p0 = r0 >= 0 ? prm.row_ptr[r0] : 0;
+      slots[0].p1 = r0 >= 0 ? prm.row_ptr[r0 + 1] : 0;
+    }
+    group_sync<true>(3, NB * 32);
+    for (int it = 0;; ++it) {
+      const volatile RowSlot* cs = slots + (it & 1);
+      if (cs->row < 0) break;
+      int nrow = -1;
+      if (tid == 0) {
+        const int sn = slot_of(it + 1);
+        if (sn < prm.nrows) nrow = __ldg(prm.order + sn);
+      }
+      const int opos = slot_of(it);
+      const bool is_long = prm.long_sum != nullptr && opos < kLongMax && (cs->p1 - cs->p0) >= kLongRow;
+      const int64_t bp1 = is_long ? cs->p0 : cs->p1;
+      const int b = it & 1;
+      QMFB_T(tb0);
+      build_row<SM, true>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k, cs->p0, bp1, cs->base,
+                          is_long ? prm.long_sum + size_t(opos) * LongRow<NT>::kLen : nullptr,
+                          reinterpret_cast<double*>(smem + SM::kOffTiles + size_t(b) * SM::kTileBytes),
+                          reinterpret_cast<double*>(smem + SM::kOffBh) + 8 * b, &tempty[b], uint32_t(((it >> 1) - 1) & 1), it >= 2,
+                          prm.tma_gather != 0);
+      mbar_arrive(&tfull[b]);  // release: this thread's tile stores are visible to the solver group that acquires
+      if (tid == 0) {
+        volatile RowSlot* ns = slots + ((it + 1) & 1);
+        ns->row = nrow;
+        ns->p0 = nrow >= 0 ? __ldg(prm.row_ptr + nrow) : 0;
+        ns->p1 = nrow >= 0 ? __ldg(prm.row_ptr + nrow + 1) : 0;
+        ns->base = cs->base + uint32_t((bp1 - cs->p0 + kChunk - 1) / kChunk);
+      }
+      group_sync<true>(3, NB * 32);  // next row slot visible; every builder is past this row's ring
+      QMFB_T(tb1);
+      QMFB_ACC(10, tb0, tb1);
+    }
+  } else {
+    // ================= solver group g: rows it = g, g + 2, ... out of tile buffer g =================
+    const int g = (warp - NB) / NS, gw = (warp - NB) % NS, gtid = gw * 32 + lane;
+    double* tiles = reinterpret_cast<double*>(smem + SM::kOffTiles + size_t(g) * SM::kTileBytes);
+    double* wt = reinterpret_cast<double*>(smem + SM::kOffW) + size_t(g) * NT * 64;
+    double* bcopy = reinterpret_cast<double*>(smem + SM::kOffB) + size_t(g) * SM::KP;
+    double* xvec = reinterpret_cast<double*>(smem + SM::kOffX) + size_t(g) * SM::KP;
+    double* rvec = reinterpret_cast<double*>(smem + SM::kOffR) + 8 * g;
+    double* fscratch = reinterpret_cast<double*>(smem + SM::kOffFs) + 16 * g;
+    const double* bhalf = reinterpret_cast<const double*>(smem + SM::kOffBh) + 8 * g;
+    for (int it = g;; it += 2) {
+      const int sl = slot_of(it);
+      if (sl >= prm.nrows) break;
+      const int row = __ldg(prm.order + sl);
+      QMFB_T(tw0);
+      mbar_wait(&tfull[g], uint32_t(it >> 1) & 1u);
+      QMFB_T(tw1);
+      QMFB_ACC_IF(g == 0 && gtid == 0, 22, tw0, tw1);
+      if (!solve_row_impl<NT, NS, QMFB_WS_TU, true>(tiles, wt, bcopy, xvec, rvec, fscratch, gw, lane, gtid, 1 + g) && lane == 0) {
+        *prm.error = 1;
+      }
+      group_sync<true>(1 + g, NS * 32);
+      // loss term: c + x^T B x - 2 x^T b with x^T B x = z^T z - lambda x^T x (WALSEngine.cpp:295-304)
+      if (gw == 0) {
+        double part = 0.0;
+        for (int i = lane; i < prm.k; i += 32) {
+          const double z = tiles[size_t(SM::tidx(i >> 3, NT)) * 64 + (i & 7) * 8 + tile_sw(i & 7)];
+          const double x = xvec[i];
+          part += z * z - prm.lambda * x * x - 2.0 * x * bcopy[i];
+        }
+        if (lane < NB) part += bhalf[lane];  // sum_s (1 + alpha r_s), WALSEngine.cpp:286
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) prm.row_loss[row] = part;
+      }
+      if (NS == 1) {
+        store_solved_row(prm, xvec, prm.row_offset + row, SM::KP, 0, lane, 0, 1);
+      } else if (gw != 0) {
+        store_solved_row(prm, xvec, prm.row_offset + row, SM::KP, gw - 1, lane, 0, NS - 1);
+      }
+      group_sync<true>(1 + g, NS * 32);  // every read of the buffer / scratch is done
+      mbar_arrive(&tempty[g]);
+      QMFB_T(tw2);
+      QMFB_ACC_IF(g == 0 && gtid == 0, 23, tw1, tw2);
+#ifdef QMFB_PROFILE_PHASES
+      if (g == 0 && gtid == 0) atomicAdd(&g_phase_cycles[15], 1ull);
+#endif
+    }
+  }
   if (prm.npeers > 0) __threadfence_system();
 }
 

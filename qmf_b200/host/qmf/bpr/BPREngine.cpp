@@ -82,6 +82,8 @@ void BPREngine::init(const std::vector<DatasetElem>& dataset) {
   QMFB_OK_OR_DIE(qmfb_bpr_set_factors(dev_, QMFB_SIDE_USER, userFactors_->getFactors().data()));
   QMFB_OK_OR_DIE(qmfb_bpr_set_factors(dev_, QMFB_SIDE_ITEM, itemFactors_->getFactors().data()));
   if (config_.useBiases) QMFB_OK_OR_DIE(qmfb_bpr_set_biases(dev_, itemFactors_->getBiases().data()));
+  // Hogwild block split: the tail of ndata mod numHogwildThreads pairs is never visited (BPREngine.cpp:156-160)
+  QMFB_OK_OR_DIE(qmfb_bpr_set_hogwild_blocks(dev_, int64_t(config_.numHogwildThreads)));
 }
 
 void BPREngine::initTest(const std::vector<DatasetElem>& testDataset) {
@@ -114,9 +116,10 @@ void BPREngine::optimize() {
   CHECK(userFactors_ && itemFactors_) << "no factor data, have you initialized the engine?";
   for (size_t epoch = 1; epoch <= config_.nepochs; ++epoch) {
     int64_t nUpdates = 0;
+    // the reference shuffles AFTER evaluate() (BPREngine.cpp:172-174): epoch 1 runs in file order
     QMFB_OK_OR_DIE(qmfb_bpr_epoch(dev_, learningRate_, config_.userLambda, config_.itemLambda, config_.biasLambda,
                                   int(config_.numNegativeSamples), deviceSeed_, uint64_t(epoch),
-                                  config_.shuffleTrainingSet ? 1 : 0, &nUpdates));
+                                  (config_.shuffleTrainingSet && epoch > 1) ? 1 : 0, &nUpdates));
     hostStale_ = true;
     evaluate(epoch);
     if (config_.decayRate < 1.0) learningRate_ *= config_.decayRate;

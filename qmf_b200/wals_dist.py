@@ -15,7 +15,7 @@ its user range and the CSC rows of its item range.  One half-step "update side S
 
 torch is used for device memory, streams and torch.distributed only.  With world == 1 no
 collective is issued.  The same class runs on CPU tensors with the `gloo` backend when a
-`kernels` object is injected (tests/test_wals_dist_cpu.py exercises the sharding/exchange logic
+`kernels` object is injected (tests/test_host_logic_cpu.py::test_sharded_wals_two_ranks_gloo exercises the sharding/exchange logic
 that way); the product path always uses the CUDA library.
 """
 import ctypes as C
@@ -71,12 +71,12 @@ class CudaKernels:
                                                ws.data_ptr(), out.data_ptr()))
 
     def solve(self, X, row_offset, Y, k, row_ptr, col, val, order, gram, alpha, lam, row_loss, loss_sum, scratch,
-              peers=()):
+              peers=(), nnz=-1):
         """peers: raw device pointers of the other ranks' replicas of X (fused all-gather)"""
         arr = (C.c_void_p * max(len(peers), 1))(*peers)
         self.capi.check(self.lib.qmfb_wals_solve_peers_dev(
             self._stream(), X.data_ptr(), X.stride(0), row_offset, Y.data_ptr(), Y.stride(0), k, row_ptr.data_ptr(),
-            col.data_ptr(), val.data_ptr(), order.data_ptr(), order.numel(), gram.data_ptr(), alpha, lam,
+            col.data_ptr(), val.data_ptr(), order.data_ptr(), order.numel(), nnz, gram.data_ptr(), alpha, lam,
             row_loss.data_ptr(), loss_sum.data_ptr(), scratch.data_ptr(), arr, len(peers)))
 
     # ---- replicas shareable between the ranks of one box (CUDA IPC) ----
@@ -235,10 +235,11 @@ class ShardedWals:
         if self.exchange == "p2p":
             self.kern.solve(self.F[side], sh["begin"], self.F[other], self.k, sh["row_ptr"], sh["col"], sh["val"],
                             sh["order"], self.gram_packed, alpha, lam, self.row_loss, self.loss_sum, self.scratch,
-                            peers=self.peers[side])
+                            peers=self.peers[side], nnz=sh["nnz"])
         else:
             self.kern.solve(self.F[side], sh["begin"], self.F[other], self.k, sh["row_ptr"], sh["col"], sh["val"],
-                            sh["order"], self.gram_packed, alpha, lam, self.row_loss, self.loss_sum, self.scratch)
+                            sh["order"], self.gram_packed, alpha, lam, self.row_loss, self.loss_sum, self.scratch,
+                            nnz=sh["nnz"])
         if events is not None:
             events["solve1"].record()
         self.launches += self.kern.launches_per_half_step

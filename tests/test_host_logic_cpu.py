@@ -89,7 +89,7 @@ class OracleKernels:
             self.O.qmfo_gram(np.ascontiguousarray(Y[rb:re].numpy()), re - rb, k, G)
         out.copy_(torch.from_numpy(G.reshape(-1)))
 
-    def solve(self, X, row_offset, Y, k, row_ptr, col, val, order, gram, alpha, lam, row_loss, loss_sum, scratch):
+    def solve(self, X, row_offset, Y, k, row_ptr, col, val, order, gram, alpha, lam, row_loss, loss_sum, scratch, nnz=-1):
         G = np.ascontiguousarray(gram.numpy().reshape(k, k))
         Yn = np.ascontiguousarray(Y.numpy())
         rp, c, v = row_ptr.numpy(), col.numpy(), val.numpy()

@@ -273,3 +273,37 @@ def test_extremely_long_row_is_built_by_many_ctas(oracle_lib):
     li_o = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, irp, ici, iv, 40.0, 0.05, NU, NI, 16)
     assert rel_err_rows(h.get_factors(0), X) < FACTOR_TOL and rel_err_rows(h.get_factors(1), Y) < FACTOR_TOL
     assert abs(lu - lu_o) <= LOSS_TOL * abs(lu_o) and abs(li - li_o) <= LOSS_TOL * abs(li_o)
+
+
+@pytest.mark.parametrize("nu,ni,nnz,k,dup", [(700, 500, 20000, 128, 0), (900, 300, 9000, 128, 11), (400, 300, 12000, 100, 0),
+                                              (500, 400, 8000, 64, 0), (300, 200, 6000, 30, 5), (260, 210, 5000, 96, 0),
+                                              (4000, 300, 60000, 128, 0)])
+def test_warp_specialised_kernel_matches_the_plain_kernel_and_the_oracle(oracle_lib, nu, ni, nnz, k, dup):
+    """wals_solve_ws_kernel (builder warps + two solver groups per SM) against the plain kernel: identical
+    factors (same per-row arithmetic: gather order, DMMA order, Cholesky order) and loss; and against the
+    oracle at the usual tolerances.  Forced through qmfb_wals_set_solve_kernel for every tile count."""
+    from qmf_b200 import capi
+    alpha, lam = 40.0, 0.05
+    out = {}
+    try:
+        for mode in (1, 2):
+            capi.check(capi.lib.qmfb_wals_set_solve_kernel(mode))
+            h, ucsr, icsr, NU, NI = _setup(nu, ni, nnz, k, seed=3 * k + nu, dup=dup)
+            h.set_factors(1, init_factors(NI, k, seed=5))
+            res = []
+            for _ in range(2):
+                lu = h.half_step(0, alpha, lam)
+                li = h.half_step(1, alpha, lam)
+                res.append((lu, li, h.get_factors(0), h.get_factors(1)))
+            out[mode] = res
+            h.close()
+    finally:
+        capi.check(capi.lib.qmfb_wals_set_solve_kernel(0))
+    X, Y = np.zeros((NU, k)), init_factors(NI, k, seed=5)
+    for e in range(2):
+        assert out[1][e][0] == out[2][e][0] and out[1][e][1] == out[2][e][1]
+        assert np.array_equal(out[1][e][2], out[2][e][2]) and np.array_equal(out[1][e][3], out[2][e][3])
+        lu_o = oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, ucsr[0], ucsr[1], ucsr[2], alpha, lam, NU, NI, 16)
+        li_o = oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, icsr[0], icsr[1], icsr[2], alpha, lam, NU, NI, 16)
+        assert rel_err_rows(out[2][e][2], X) < FACTOR_TOL and rel_err_rows(out[2][e][3], Y) < FACTOR_TOL
+        assert abs(out[2][e][0] - lu_o) <= LOSS_TOL * abs(lu_o) and abs(out[2][e][1] - li_o) <= LOSS_TOL * abs(li_o)

@@ -12,7 +12,8 @@ kp = K.padded_k(k)
 names = ["build", "tile store+b", "factor diag (warp0)", "panel (b)", "wait top-of-step", "wait after panel", "diag tile update",
          "cholesky total", "back substitution", "loss/store/next", "row total", "  build: issue_one", "  build: wait full",
          "  build: chunk_mma", "  build: b-acc + arrive", "(rows)", "  build: prologue issue", "  build: gram load", "  build: chunk loop",
-         "  build: b partial store", "  build: end barrier", "  build: tile store"]
+         "  build: b partial store", "  build: end barrier / wait tile buffer", "  build: tile store", "ws solver: wait for tiles",
+         "ws solver: solve+loss+store"]
 K.lib.qmfb_debug_set_flags(int(os.environ.get("EXP_FLAGS", "0")))
 for spec in sys.argv[1:]:
     nrows, nnz_row, ncols = (int(x) for x in spec.split(","))
