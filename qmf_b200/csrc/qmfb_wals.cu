@@ -105,7 +105,8 @@ static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_su
       })) return rc;
   QMFB_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(int32_t), st));
   if (prm.nrows > 0) {
-    const int grid = int(std::min<int64_t>(grid_cap, prm.nrows));
+    static const int grid_env = getenv("QMFB_GRID_CAP") ? atoi(getenv("QMFB_GRID_CAP")) : 0;  // measurement switch
+    const int grid = int(std::min<int64_t>(grid_env > 0 ? std::min(grid_env, grid_cap) : grid_cap, prm.nrows));
     // extremely long rows at the head of `order` are summed by many CTAs ahead of the solve kernel
     // (two empty launches when there is none); stream-ordered scratch, freed after the kernel
     constexpr int kLen = LongRow<NT>::kLen;
@@ -126,7 +127,8 @@ static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_su
     const int mode = g_solve_kernel.load();
     if (mode == 1) ws = false;
     if (mode == 2) ws = true;
-    if (ws) {
+    if constexpr (NT < 8) ws = false;  // a solver group needs a chain warp and at least one sweeper (NT / 4 >= 2 warps)
+    if constexpr (NT >= 8) if (ws) {
       using WS = WalsSmemWs<NT>;
       static PerDeviceCfg wcfg;
       int wcap = 0;
@@ -143,9 +145,8 @@ static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_su
         return rc;
       }
       wals_solve_ws_kernel<NT><<<int(std::min<int64_t>(wcap, prm.nrows)), WS::NTHREADS, WS::kBytes, st>>>(run);
-    } else {
-      wals_solve_kernel<NT><<<grid, SM::NTHREADS, SM::kBytes, st>>>(run);
     }
+    if (!ws) wals_solve_kernel<NT><<<grid, SM::NTHREADS, SM::kBytes, st>>>(run);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(long_buf, st);
     QMFB_CUDA(e);

@@ -36,7 +36,7 @@ struct WalsSmemBig {
   static constexpr size_t kOffX = kOffB + size_t(KP) * 8;
   static constexpr size_t kOffR = kOffX + size_t(KP) * 8;
   static constexpr size_t kOffFs = kOffR + 64;
-  static constexpr size_t kOffBh = kOffFs + 128;                               // sum of (1 + alpha r)
+  static constexpr size_t kOffBh = kOffFs + 256;                               // sum of (1 + alpha r)
   static constexpr size_t kBytes = kOffBh + 64;
   __host__ __device__ static constexpr int tidx(int I, int J) { return I * (NT + 1) - I * (I - 1) / 2 + (J - I); }
   __host__ __device__ static constexpr int gidx(int I, int J) { return I * NT - I * (I - 1) / 2 + (J - I); }
@@ -143,6 +143,11 @@ __global__ void __launch_bounds__(WalsSmemBig<NT>::NTHREADS, 1) wals_solve_big_k
   double* tiles = ws + size_t(blockIdx.x) * SM::NTILE * 64;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   constexpr int PPR = SM::KP / 2;
+  if (tid == 0) {
+    solve_bars_init<SM::NWARPS>(reinterpret_cast<double*>(smem + SM::kOffFs));
+    mbar_fence_init();
+  }
+  __syncthreads();
 
   for (int slot = blockIdx.x; slot < prm.nrows; slot += gridDim.x) {
     const int row = prm.order[slot];

@@ -139,8 +139,8 @@ struct WalsSmem {
   static constexpr size_t kOffB = kOffW + size_t(NT) * 64 * 8;               // b copy (KP)
   static constexpr size_t kOffX = kOffB + size_t(KP) * 8;                    // x (KP)
   static constexpr size_t kOffR = kOffX + size_t(KP) * 8;                    // back-substitution rhs (8)
-  static constexpr size_t kOffFs = kOffR + 64;                               // pivot-row broadcast scratch (16 doubles)
-  static constexpr size_t kOffBh = kOffFs + 128;                             // per-warp partial sum of (1 + alpha r) (NWARPS, padded to 8)
+  static constexpr size_t kOffFs = kOffR + 64;                               // solve barriers F/S/G (8 doubles) + pivot-row scratch (16 doubles)
+  static constexpr size_t kOffBh = kOffFs + 256;                             // per-warp partial sum of (1 + alpha r) (NWARPS, padded to 8)
   static constexpr size_t kOffBar = kOffBh + 64;                             // full[kStages], empty[kStages]
   static constexpr size_t kOffRow = kOffBar + size_t(kStages) * 16;          // 2 row slots x 32 bytes
   static constexpr size_t kBytes = kOffRow + 64;
@@ -184,8 +184,8 @@ struct WalsSmemWs {
   static constexpr size_t kOffB = kOffW + 2 * size_t(NT) * 64 * 8;               // 2 x b copy (KP)
   static constexpr size_t kOffX = kOffB + 2 * size_t(KP) * 8;                    // 2 x x (KP)
   static constexpr size_t kOffR = kOffX + 2 * size_t(KP) * 8;                    // 2 x back-substitution rhs (8)
-  static constexpr size_t kOffFs = kOffR + 2 * 64;                               // 2 x pivot-row scratch (16 doubles)
-  static constexpr size_t kOffBh = kOffFs + 2 * 128;                             // 2 x partial sums of (1 + alpha r) (8)
+  static constexpr size_t kOffFs = kOffR + 2 * 64;                               // 2 x (solve barriers + pivot-row scratch), 32 doubles each
+  static constexpr size_t kOffBh = kOffFs + 2 * 256;                             // 2 x partial sums of (1 + alpha r) (8)
   static constexpr size_t kOffBar = kOffBh + 2 * 64;                             // full[kRing], empty[kRing], tfull[2], tempty[2]
   static constexpr size_t kOffRow = kOffBar + ((size_t(2 * kRing + 4) * 8 + 15) / 16) * 16;  // 2 row slots x 32 bytes
   static constexpr size_t kBytes = kOffRow + 64;
@@ -601,6 +601,71 @@ __device__ __noinline__ bool factor_diag_tile(double a0, double a1, double* wtil
   return ok;
 }
 
+// Same contract as factor_diag_tile (A = U^T U, W = inv(U)^T to wtile), but the pivot-to-pivot chain never
+// leaves the register file: the TENSOR CORE does the data movement.  For an accumulator fragment X (lane
+// 4n+q holds X[n][2q], X[n][2q+1]) slot h used as the A operand of an m8n8k4 DMMA is A[i][k] = X[i][2k+h] and
+// used as the B operand it is B[k][m] = X[m][2k+h] - so for a SYMMETRIC trailing block the lanes with
+// q == j/2 already hold column j of the tile (slot j%2) exactly where the DMMA wants both operands of the
+// rank-1 update  C <- C pn - (u sc) u^T  (u = C[., j], rows > j; pn, sc as in factor_diag_tile).  No shared
+// memory, no __syncwarp, and ONE shuffle per pivot (the pivot itself, needed by every lane for the exact
+// power-of-two normalisation): the dependent chain per pivot is shuffle -> DMUL -> DMMA instead of
+// store -> barrier -> 4 loads -> barrier -> DMUL -> DFMA -> DMUL.  The inverse rides along TRANSPOSED
+// (T = E^T, T[n][r] <- T[n][r] s_r - T[n][j] (u_r sc)): its A operand is column j of T, its B operand the same
+// u - also local.  Only the part of C below the diagonal (column j, rows > j) is ever read.
+// Returns false on a non-positive pivot (reference: dsysv info != 0, qmf/Matrix.cpp:94).
+__device__ __noinline__ bool factor_diag_tile_mma(double c0, double c1, double* wtile, int lane) {
+  const int n = lane >> 2, q = lane & 3;
+  double t0 = (2 * q == n) ? 1.0 : 0.0, t1 = (2 * q + 1 == n) ? 1.0 : 0.0;  // T = E^T = I
+  double S = 1.0, prS0 = 1.0, prS1 = 1.0;  // prS_h = p_r S_r for r = 2q + h (columns of T this lane holds)
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const double cj = (j & 1) ? c1 : c0;                         // lanes q == j/2: C[n][j]
+    const double p = __shfl_sync(0xffffffffu, cj, 4 * j + (j >> 1));  // C[j][j]
+    ok = ok && (p > 0.0);
+    const int hi = __double2hiint(p), lo = __double2loint(p);
+    const double pn = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, lo);
+    const double sc = __hiloint2double((2046 - ((hi >> 20) & 0x7ff)) << 20, 0);
+    if ((j & 1) == 0) {
+      if (2 * q == j) prS0 = p * S;
+    } else {
+      if (2 * q + 1 == j) prS1 = p * S;
+    }
+    S *= pn;
+    const bool colj = q == (j >> 1);
+    const double u = (colj && n > j) ? cj : 0.0;                 // u_n, rows below the pivot
+    const double tj = colj ? ((j & 1) ? t1 : t0) : 0.0;          // T[n][j]
+    const double us = u * sc;
+    const double sr = n > j ? pn : 1.0;                          // live rows of C
+    double c[2] = {c0 * sr, c1 * sr};
+    double t[2] = {t0 * (2 * q > j ? pn : 1.0), t1 * (2 * q + 1 > j ? pn : 1.0)};  // live columns of T
+    dmma(c, -us, u);
+    dmma(t, -tj, us);
+    c0 = c[0]; c1 = c[1];
+    t0 = t[0]; t1 = t[1];
+  }
+  {  // last pivot C[7][7] (lane 31, second slot): nothing left to eliminate
+    const double p7 = __shfl_sync(0xffffffffu, c1, 31);
+    ok = ok && (p7 > 0.0);
+    if (q == 3) prS1 = p7 * S;
+  }
+  // W[r][n] = T[n][r] rsqrt(p_r S_r): this lane holds rows r = 2q, 2q + 1 of W at column n
+  wtile[(2 * q) * 8 + (n ^ tile_sw(2 * q))] = t0 * rsqrt(prS0);
+  wtile[(2 * q + 1) * 8 + (n ^ tile_sw(2 * q + 1))] = t1 * rsqrt(prS1);
+  return ok;
+}
+
+#ifndef QMFB_FACTOR_MMA
+#define QMFB_FACTOR_MMA 1   // 1: factor_diag_tile_mma (tensor-core broadcast), 0: factor_diag_tile (shared-memory broadcast)
+#endif
+__device__ __forceinline__ bool factor_tile(double a0, double a1, double* wtile, double* scratch, int lane) {
+#if QMFB_FACTOR_MMA
+  return factor_diag_tile_mma(a0, a1, wtile, lane);
+#else
+  return factor_diag_tile(a0, a1, wtile, scratch, lane);
+#endif
+}
+
 #ifdef QMFB_PROFILE_PHASES
 // debug build only: thread 0 of every CTA accumulates clock64() deltas per phase into
 // g_phase_cycles[phase] (build, tile store, factor (warp 0), panel, trailing/wait, back
@@ -835,114 +900,188 @@ struct SolveDims {  // the names the body of solve_row_impl was written against
 
 // NW warps (warp = 0 .. NW-1, tid = 0 .. 32 NW - 1 inside the group; 32 NW >= 8 NT) solve the row whose
 // tiles are at `tiles`; wt / bcopy / xvec / rvec / fscratch are the group's scratch areas.
+//
+// The Cholesky is DECOUPLED: warp 0 (the "chain" warp) owns the critical path - the 8 NT dependent pivots - and
+// never waits at a block barrier.  Per step I it publishes W_I = inv(U_II)^T (mbarrier F), computes the one panel
+// tile it needs itself, U(I,I+1) = W_I A(I,I+1), updates the next diagonal tile with it in registers and goes
+// straight into its factorisation.  The other warps ("sweepers") follow one step behind: wait for W_I, panel of
+// their columns, a barrier among themselves (mbarrier S, on which the chain warp only ARRIVES after storing its
+// panel tile), then the trailing update - FIRST the two tiles the chain warp needs next, (I+1,I+2) and (I+2,I+2),
+// signalled on mbarrier G, then the rest.  The chain warp therefore waits only for data (G of the previous sweep,
+// complete long before it is needed); with block barriers it spent ~1.0k of every ~3.3k-cycle step waiting for the
+// panel and the barriers (tools/exp_phases.py).  Every barrier completes exactly NT (even) times per row, so the
+// phase parities are those of the step index.  mbarrier arrive/wait have release/acquire semantics at CTA scope:
+// they order the shared- (or, k > 128, global-) memory tile traffic between the warps.
+constexpr int kSolveBars = 3;  // F, S, G: 8 bytes each at the head of the group's `fscratch` (16 doubles)
+template <int NW>
+__device__ __forceinline__ void solve_bars_init(double* fscratch) {
+  // one thread, before the group's first row (followed by a barrier of the group / the CTA)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fscratch);
+  constexpr int npri = NW - 1 >= 2 ? 2 : 1;
+  mbar_init(&bar[0], 32);            // F: the chain warp's 32 lanes
+  mbar_init(&bar[1], NW * 32);       // S: everyone arrives, the sweepers wait
+  mbar_init(&bar[2], 32 * npri);     // G: the warps that update the two priority tiles
+}
+
 template <int NT, int NW, int TU, bool NAMED>
 __device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* bcopy, double* xvec, double* rvec, double* fscratch,
                                             int warp, int lane, int tid, int bar_id) {
   using SM = SolveDims<NT, NW>;
   static_assert(NW * 32 >= NT * 8, "one thread per unknown in the back substitution");
+  static_assert(NW >= 2 && NT % 2 == 0, "a chain warp plus at least one sweeper; even number of steps");
   const int fo = tile_frag_off(lane);                        // operand-fragment offset inside a tile
   const int fw = (lane >> 2) * 8 + ((lane & 3) ^ tile_sw(lane >> 2));  // same for the transposed W tiles; k+4 half at fw ^ 4
   const int co = tile_acc_off(lane);                         // accumulator-fragment offset
+  uint64_t* barF = reinterpret_cast<uint64_t*>(fscratch);
+  uint64_t* barS = barF + 1;
+  uint64_t* barG = barF + 2;
+  constexpr int nw = NW - 1;                                 // sweepers
+  constexpr int npri = nw >= 2 ? 2 : 1;
   QMFB_T(tp1);
   // keep a copy of b (column 0 of the b tiles) for the loss before the factorisation overwrites it with z
   if (tid < SM::KP) bcopy[tid] = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
-  // ---- blocked Cholesky, panel width 8; forward substitution rides along in column NT ------
+  // every thread has its copy before any b tile is overwritten: the first panel tile written is (0, 1) by the chain
+  // warp, b tiles (J == NT) only after the sweepers have seen W_0; NT >= 4, so one barrier of the group suffices
+  group_sync<NAMED>(bar_id, NW * 32);
   bool ok = true;
   QMFB_T(tp2);
   QMFB_ACC_IF(tid == 0 && bar_id <= 1, 1, tp1, tp2);
   if (warp == 0) {
-    const double2 a = *reinterpret_cast<const double2*>(tiles + size_t(SM::tidx(0, 0)) * 64 + co);
-    ok = factor_diag_tile(a.x, a.y, wt, fscratch, lane);
-  }
-  QMFB_T(tp3);
-  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 2, tp2, tp3);
-  for (int I = 0; I < NT; ++I) {
-    QMFB_T(ts0);
-    group_sync<NAMED>(bar_id, NW * 32);  // W_I ready, row I of tiles final up to panel I-1
-    QMFB_T(ts1);
-    QMFB_ACC_IF(tid == 0 && bar_id <= 1, 4, ts0, ts1);
-    // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+1 .. NT
+    // ================= chain warp =================
     {
-      const double w0 = wt[I * 64 + fw], w1 = wt[I * 64 + (fw ^ 4)];
-      for (int J = I + 1 + warp; J <= NT; J += SM::NWARPS) {
-        double* t = tiles + size_t(SM::tidx(I, J)) * 64;
+      const double2 a = *reinterpret_cast<const double2*>(tiles + size_t(SM::tidx(0, 0)) * 64 + co);
+      ok = factor_tile(a.x, a.y, wt, fscratch + 8, lane);
+    }
+    for (int I = 0; I < NT; ++I) {
+      QMFB_T(ts0);
+      mbar_arrive(barF);                                     // F(I): this lane's part of W_I is published
+      __syncwarp();                                          // ... and visible to the other lanes of this warp
+      if (I > 0) mbar_wait(barG, uint32_t(I - 1) & 1u);      // (I, I+1) and (I+1, I+1) final through sweep I-1
+      QMFB_T(ts1);
+      QMFB_ACC_IF(tid == 0 && bar_id <= 1, 4, ts0, ts1);
+      double* t = tiles + size_t(SM::tidx(I, I + 1)) * 64;
+      {
+        const double w0 = wt[I * 64 + fw], w1 = wt[I * 64 + (fw ^ 4)];
         double c[2] = {0.0, 0.0};
         dmma(c, w0, t[fo]);
         dmma(c, w1, t[fo + 32]);
         __syncwarp();
         *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
       }
-    }
-    QMFB_T(ts2);
-    QMFB_ACC_IF(tid == 0 && bar_id <= 1, 3, ts1, ts2);
-    if (I == NT - 1) break;
-    group_sync<NAMED>(bar_id, NW * 32);
-    QMFB_T(ts3);
-    QMFB_ACC_IF(tid == 0 && bar_id <= 1, 5, ts2, ts3);
-    // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT.
-    //     One warp updates the next diagonal tile first and factors it right away (look-ahead)
-    //     while the other warps sweep the rest (kTU tiles in flight each).
-    const int tstart = SM::tidx(I + 1, I + 1);
-    const double* urow = tiles + size_t(SM::tidx(I, I)) * 64;  // tile (I, J) = urow + (J - I) * 64
-    constexpr int dwarp = 0;
-    const int nw = SM::NWARPS > 1 ? SM::NWARPS - 1 : 1;
-    const int wslot = SM::NWARPS > 1 ? warp - 1 : 0;
-    if (SM::NWARPS == 1 || warp == dwarp) {
-      double* t = tiles + size_t(tstart) * 64;
-      const double* u = urow + 64;
-      double2 cv = *reinterpret_cast<double2*>(t + co);
+      mbar_arrive(barS);                                     // S(I): the panel tile (I, I+1) is published
+      QMFB_T(ts2);
+      QMFB_ACC_IF(tid == 0 && bar_id <= 1, 3, ts1, ts2);
+      if (I == NT - 1) break;
+      __syncwarp();
+      const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(SM::tidx(I + 1, I + 1)) * 64 + co);
       double c[2] = {cv.x, cv.y};
-      const double u0 = u[fo], u1 = u[fo + 32];
+      const double u0 = t[fo], u1 = t[fo + 32];
       dmma(c, -u0, u0);
       dmma(c, -u1, u1);
       QMFB_T(tf0);  // the updated tile goes to the factor in registers (same fragment layout); U_II itself is never read again
-      ok = factor_diag_tile(c[0], c[1], wt + (I + 1) * 64, fscratch, lane) && ok;
+      ok = factor_tile(c[0], c[1], wt + (I + 1) * 64, fscratch + 8, lane) && ok;
       QMFB_T(tf1);
       QMFB_ACC_IF(tid == 0 && bar_id <= 1, 2, tf0, tf1);
-      QMFB_ACC_IF(tid == 0 && bar_id <= 1, 6, ts3, tf0);
+      QMFB_ACC_IF(tid == 0 && bar_id <= 1, 6, ts2, tf0);
+      // every sweeper has observed F(I) (it arrived on S(I) afterwards): F may advance without a phase wrapping
+      mbar_wait(barS, uint32_t(I) & 1u);
+      QMFB_T(tf2);
+      QMFB_ACC_IF(tid == 0 && bar_id <= 1, 5, tf1, tf2);
     }
+  } else {
+    // ================= sweepers =================
+    const int wslot = warp - 1;
+    for (int I = 0; I < NT; ++I) {
+      mbar_wait(barF, uint32_t(I) & 1u);                     // W_I
+      // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+2 .. NT  ((I, I+1) is the chain warp's)
+      {
+        const double w0 = wt[I * 64 + fw], w1 = wt[I * 64 + (fw ^ 4)];
+        for (int J = I + 2 + wslot; J <= NT; J += nw) {
+          double* t = tiles + size_t(SM::tidx(I, J)) * 64;
+          double c[2] = {0.0, 0.0};
+          dmma(c, w0, t[fo]);
+          dmma(c, w1, t[fo + 32]);
+          __syncwarp();
+          *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
+        }
+      }
+      mbar_arrive(barS);
+      if (I == NT - 1) {
+        if (wslot < npri) mbar_arrive(barG);                 // NT-th completion of G (nobody waits for it): parity stays even
+        break;
+      }
+      mbar_wait(barS, uint32_t(I) & 1u);                     // the whole panel row I is in place
+      // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT, except (I+1, I+1) (chain warp)
+      const int tstart = SM::tidx(I + 1, I + 1);
+      const double* urow = tiles + size_t(SM::tidx(I, I)) * 64;  // tile (I, J) = urow + (J - I) * 64
+      const int p1 = tstart + 1;                               // (I+1, I+2): exists (I <= NT - 2)
+      const int p2 = tstart + (NT - I);                        // (I+2, I+2): exists iff I <= NT - 3
+      const bool has_p2 = I <= NT - 3;
+      auto update_one = [&](int ti, int j1, int j2) {
+        const double* ta = urow + (j1 - I) * 64;
+        const double* tb = urow + (j2 - I) * 64;
+        double* tc = tiles + size_t(ti) * 64 + co;
+        const double2 cv = *reinterpret_cast<const double2*>(tc);
+        double c[2] = {cv.x, cv.y};
+        const double a0 = -ta[fo], a1 = -ta[fo + 32], b0 = tb[fo], b1 = tb[fo + 32];
+        dmma(c, a0, b0);
+        dmma(c, a1, b1);
+        *reinterpret_cast<double2*>(tc) = make_double2(c[0], c[1]);
+      };
+      if (wslot == 0) update_one(p1, I + 1, I + 2);
+      if (wslot == npri - 1 && has_p2) update_one(p2, I + 2, I + 2);
+      if (wslot < npri) {
+        __syncwarp();
+        mbar_arrive(barG);                                     // G(I)
+      }
 #ifdef QMFB_PROFILE_PHASES
-    if ((g_debug_flags & 1) == 0)
+      if ((g_debug_flags & 1) == 0)
 #endif
-    if (SM::NWARPS == 1 || warp != dwarp) {
-      // flat enumeration of the trailing tiles (contiguous in storage); (J1, J2) decoded incrementally
-      int J1 = I + 1, off = 1 + wslot;  // position `off` inside row J1 (row J1 has NT - J1 + 1 tiles)
-      for (int e = tstart + 1 + wslot; e < SM::NTILE; e += TU * nw) {
-        // straight-line body: out-of-range slots of the last sweep recompute a valid tile and skip the store
-        double c[TU][2], ua[TU][2], ub[TU][2];
+      {
+        // the remaining tiles: flat storage positions tstart + 2 .. NTILE - 1 except p2, dealt round-robin;
+        // (J1, J2) decoded incrementally.  Straight-line body: out-of-range slots of the last pass recompute a
+        // valid tile and skip the store.
+        const int nrest = SM::NTILE - (tstart + 2) - (has_p2 ? 1 : 0);
+        int J1 = I + 1, rowstart = tstart, rowlen = NT - I;    // row J1 holds tiles (J1, J1) .. (J1, NT)
+        for (int d0 = wslot; d0 < nrest; d0 += TU * nw) {
+          double c[TU][2], ua[TU][2], ub[TU][2];
+          int tis[TU];
 #pragma unroll
-        for (int q = 0; q < TU; ++q) {
-          const int ti = e + q * nw;
-          const bool v = ti < SM::NTILE;
-          if (v) {
-            while (off >= NT - J1 + 1) {
-              off -= NT - J1 + 1;
-              ++J1;
+          for (int q = 0; q < TU; ++q) {
+            const int d = d0 + q * nw;
+            const bool v = d < nrest;
+            int e = tstart + 2 + d;
+            if (has_p2 && e >= p2) ++e;
+            if (v) {
+              while (e >= rowstart + rowlen) {
+                rowstart += rowlen;
+                --rowlen;
+                ++J1;
+              }
             }
+            tis[q] = v ? e : -1;
+            const double* ta = urow + (v ? J1 - I : 1) * 64;
+            const double* tb = urow + (v ? J1 + (e - rowstart) - I : 1) * 64;
+            const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(v ? e : tstart) * 64 + co);
+            c[q][0] = cv.x; c[q][1] = cv.y;
+            ua[q][0] = -ta[fo]; ua[q][1] = -ta[fo + 32];
+            ub[q][0] = tb[fo]; ub[q][1] = tb[fo + 32];
           }
-          const double* ta = urow + (v ? J1 - I : 1) * 64;
-          const double* tb = urow + (v ? J1 + off - I : 1) * 64;
-          const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(v ? ti : tstart) * 64 + co);
-          c[q][0] = cv.x; c[q][1] = cv.y;
-          ua[q][0] = -ta[fo]; ua[q][1] = -ta[fo + 32];
-          ub[q][0] = tb[fo]; ub[q][1] = tb[fo + 32];
-          off += nw;
-        }
 #pragma unroll
-        for (int q = 0; q < TU; ++q) {
-          dmma(c[q], ua[q][0], ub[q][0]);
-          dmma(c[q], ua[q][1], ub[q][1]);
-        }
+          for (int q = 0; q < TU; ++q) {
+            dmma(c[q], ua[q][0], ub[q][0]);
+            dmma(c[q], ua[q][1], ub[q][1]);
+          }
 #pragma unroll
-        for (int q = 0; q < TU; ++q) {
-          const int ti = e + q * nw;
-          if (ti < SM::NTILE) *reinterpret_cast<double2*>(tiles + size_t(ti) * 64 + co) = make_double2(c[q][0], c[q][1]);
+          for (int q = 0; q < TU; ++q) {
+            if (tis[q] >= 0) *reinterpret_cast<double2*>(tiles + size_t(tis[q]) * 64 + co) = make_double2(c[q][0], c[q][1]);
+          }
         }
       }
     }
   }
   QMFB_T(tp4);
-  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 7, tp3, tp4);
+  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 7, tp2, tp4);
 
   // ---- back substitution U x = z: thread t < KP keeps r_t in a register; per block step one
   //      8x8 mat-vec by inv(U_JJ) and one rank-8 update of the rows above -----------------------
@@ -1023,6 +1162,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
       mbar_init(&full[s], 32 + kChunk);  // gathering warp: one deferred cp.async arrival per lane + weight writers
       mbar_init(&empty[s], SM::NWARPS);
     }
+    solve_bars_init<SM::NWARPS>(fscratch);
     mbar_fence_init();
   }
 
@@ -1141,6 +1281,7 @@ __global__ void __launch_bounds__(WalsSmemWs<NT>::NTHREADS, 1) wals_solve_ws_ker
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], NB * 32);
       mbar_init(&tempty[b], NS * 32);
+      solve_bars_init<NS>(reinterpret_cast<double*>(smem + SM::kOffFs) + 32 * b);
     }
     mbar_fence_init();
   }
@@ -1204,7 +1345,7 @@ __global__ void __launch_bounds__(WalsSmemWs<NT>::NTHREADS, 1) wals_solve_ws_ker
     double* bcopy = reinterpret_cast<double*>(smem + SM::kOffB) + size_t(g) * SM::KP;
     double* xvec = reinterpret_cast<double*>(smem + SM::kOffX) + size_t(g) * SM::KP;
     double* rvec = reinterpret_cast<double*>(smem + SM::kOffR) + 8 * g;
-    double* fscratch = reinterpret_cast<double*>(smem + SM::kOffFs) + 16 * g;
+    double* fscratch = reinterpret_cast<double*>(smem + SM::kOffFs) + 32 * g;
     const double* bhalf = reinterpret_cast<const double*>(smem + SM::kOffBh) + 8 * g;
     for (int it = g;; it += 2) {
       const int sl = slot_of(it);

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include <qmf/Types.h>
+#include <qmf/utils/FriendTest.h>
 
 namespace qmf {
 
@@ -40,6 +41,10 @@ class DatasetReader {
   std::string fileName_;
   bool touched_ = false;  // readOne() has consumed part of the stream
   std::string line_;
+
+  FRIEND_TEST(DatasetReader, readOne);
+  FRIEND_TEST(DatasetReader, readOneBadFormat);
+  FRIEND_TEST(DatasetReader, readAll);
 };
 
 }  // namespace qmf

@@ -14,18 +14,53 @@
 
 namespace qmf {
 
-void Engine::initAvgTestData(TestData& out, const std::vector<DatasetElem>& testDataset, const IdIndex& userIndex,
+void Engine::selectTestUsers(std::vector<size_t>& users, const std::vector<DatasetElem>& testDataset, const IdIndex& userIndex,
                              const IdIndex& itemIndex, size_t numTestUsers, int32_t seed) {
+  // Engine.cpp:35-50 of the reference: unordered_set iteration order, then mt19937(seed) shuffle + truncation
   std::unordered_set<size_t> seen;
   for (const auto& e : testDataset) {
     const size_t u = userIndex.idx(e.userId), p = itemIndex.idx(e.itemId);
     if (u != IdIndex::missingIdx && p != IdIndex::missingIdx) seen.insert(u);
   }
-  out.users.assign(seen.begin(), seen.end());
-  if (numTestUsers > 0 && numTestUsers < out.users.size()) {
-    std::shuffle(out.users.begin(), out.users.end(), std::mt19937(seed));
-    out.users.resize(numTestUsers);
+  users.assign(seen.begin(), seen.end());
+  if (numTestUsers > 0 && numTestUsers < users.size()) {
+    std::shuffle(users.begin(), users.end(), std::mt19937(seed));
+    users.resize(numTestUsers);
   }
+}
+
+void Engine::initAvgTestData(std::vector<size_t>& testUsers, std::vector<std::vector<Double>>& testLabels,
+                             std::vector<std::vector<Double>>& testScores, const std::vector<DatasetElem>& testDataset,
+                             const IdIndex& userIndex, const IdIndex& itemIndex, const size_t numTestUsers, const int32_t seed) {
+  selectTestUsers(testUsers, testDataset, userIndex, itemIndex, numTestUsers, seed);
+  std::vector<int64_t> slot(userIndex.size(), -1);
+  for (size_t t = 0; t < testUsers.size(); ++t) slot[testUsers[t]] = int64_t(t);
+  testLabels.assign(testUsers.size(), std::vector<Double>(itemIndex.size(), 0.0));
+  testScores.assign(testUsers.size(), std::vector<Double>(itemIndex.size(), 0.0));
+  for (const auto& e : testDataset) {
+    const size_t u = userIndex.idx(e.userId), i = itemIndex.idx(e.itemId);
+    if (u == IdIndex::missingIdx || i == IdIndex::missingIdx || slot[u] < 0) continue;
+    testLabels[size_t(slot[u])][i] = e.value;
+  }
+}
+
+void Engine::computeTestScores(std::vector<std::vector<Double>>& testScores, const std::vector<size_t>& testUsers,
+                               const FactorData& userFactors, const FactorData& itemFactors, ParallelExecutor& parallel) {
+  // score = bias + sum_f p_uf q_if, accumulated in factor order (Engine.cpp:85-91)
+  parallel.execute(testUsers.size(), [&](const size_t t) {
+    const size_t u = testUsers[t];
+    std::vector<Double>& row = testScores[t];
+    for (size_t i = 0; i < itemFactors.nelems(); ++i) {
+      Double acc = itemFactors.withBiases() ? itemFactors.biasAt(i) : 0.0;
+      for (size_t f = 0; f < userFactors.nfactors(); ++f) acc += userFactors.at(u, f) * itemFactors.at(i, f);
+      row[i] = acc;
+    }
+  });
+}
+
+void Engine::initAvgTestData(TestData& out, const std::vector<DatasetElem>& testDataset, const IdIndex& userIndex,
+                             const IdIndex& itemIndex, size_t numTestUsers, int32_t seed) {
+  selectTestUsers(out.users, testDataset, userIndex, itemIndex, numTestUsers, seed);
   // slot of a user idx in `users` (dense table instead of the reference's unordered_map, Engine.cpp:53-60)
   std::vector<int64_t> slot(userIndex.size(), -1);
   for (size_t t = 0; t < out.users.size(); ++t) slot[out.users[t]] = int64_t(t);

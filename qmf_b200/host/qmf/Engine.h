@@ -12,7 +12,9 @@
 #include <qmf/DatasetReader.h>
 #include <qmf/FactorData.h>
 #include <qmf/metrics/Metrics.h>
+#include <qmf/utils/FriendTest.h>
 #include <qmf/utils/IdIndex.h>
+#include <qmf/utils/ParallelExecutor.h>
 
 namespace qmf {
 
@@ -52,9 +54,28 @@ class Engine {
   static void computeAndRecordTestAvgMetrics(MetricsEngine& metrics, size_t epoch, const TestData& test, size_t nItems,
                                              size_t nthreads, const RankFn& rank);
 
+  // The reference's own (protected, static) helpers with their dense nT x nitems vectors
+  // (qmf/Engine.h:66-82, Engine.cpp:27-96), kept so that code written against the reference compiles.  Same test
+  // users in the same order as the TestData overload; labels hold the value of the LAST test line of a
+  // (user, item).  The engines here never call them: evaluation runs on the GPU against resident factors
+  // (computeAndRecordTestAvgMetrics).
+  static void initAvgTestData(std::vector<size_t>& testUsers, std::vector<std::vector<Double>>& testLabels,
+                              std::vector<std::vector<Double>>& testScores, const std::vector<DatasetElem>& testDataset,
+                              const IdIndex& userIndex, const IdIndex& itemIndex, const size_t numTestUsers = 0,
+                              const int32_t seed = 0);
+  static void computeTestScores(std::vector<std::vector<Double>>& testScores, const std::vector<size_t>& testUsers,
+                                const FactorData& userFactors, const FactorData& itemFactors, ParallelExecutor& parallel);
+
   // "<id>[ <bias>] <f0> ... <fk-1>\n", fixed, 9 decimals (qmf/Engine.cpp:98-122)
   static void saveFactors(const FactorData& factorData, const IdIndex& index, const std::string& fileName);
   static void saveFactors(const FactorData& factorData, const IdIndex& index, std::ostream& out);
+
+ private:
+  static void selectTestUsers(std::vector<size_t>& users, const std::vector<DatasetElem>& testDataset, const IdIndex& userIndex,
+                              const IdIndex& itemIndex, size_t numTestUsers, int32_t seed);
+  FRIEND_TEST(Engine, initAvgTestData);
+  FRIEND_TEST(Engine, computeTestScores);
+  FRIEND_TEST(Engine, saveFactors);
 };
 
 }  // namespace qmf

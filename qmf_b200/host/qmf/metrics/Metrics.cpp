@@ -47,6 +47,40 @@ bool MetricsManager::exists(const std::string& name) const {
   return lookup(name, s);
 }
 
+bool MetricsManager::initFromName(const std::string& name) const {
+  MetricSpec spec;
+  if (!lookup(name, spec)) return false;
+  std::lock_guard<std::mutex> lock(mu_);
+  if (metrics_.find(name) == metrics_.end()) metrics_.emplace(name, std::make_unique<Metric>(spec));
+  return true;
+}
+
+const std::unique_ptr<Metric>& MetricsManager::getMetric(const std::string& name) const {
+  static const std::unique_ptr<Metric> none;
+  if (!initFromName(name)) return none;
+  std::lock_guard<std::mutex> lock(mu_);
+  return metrics_.find(name)->second;  // node-based map: the reference stays valid across later insertions
+}
+
+Double Metric::compute(const std::vector<Double>& labels, const std::vector<Double>& scores) const {
+  return computeMetric(spec_, labels, scores);
+}
+
+Double Metric::compute(const std::vector<std::vector<Double>>& labels, const std::vector<std::vector<Double>>& scores) const {
+  CHECK_EQ(labels.size(), scores.size());
+  std::vector<Double> perUser(labels.size());
+  for (size_t t = 0; t < labels.size(); ++t) perUser[t] = compute(labels[t], scores[t]);
+  return averageOverUsers(perUser, 0);
+}
+
+Double Metric::compute(const std::vector<std::vector<Double>>& labels, const std::vector<std::vector<Double>>& scores,
+                       ParallelExecutor& parallel) const {
+  CHECK_EQ(labels.size(), scores.size());
+  std::vector<Double> perUser(labels.size());
+  parallel.execute(labels.size(), [&](const size_t t) { perUser[t] = compute(labels[t], scores[t]); });
+  return averageOverUsers(perUser, parallel.nthreads());
+}
+
 namespace {
 // position (0-based) in the reference's ranking (score descending, positives first on ties) of
 // the q-th positive in ascending-score order: negatives that outscore it + positives above it

@@ -1,3 +1,4 @@
 set -x
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest4.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_pytest4.log
-tail -30 gpurun_out/r02_pytest4.log
+export QMFB_LIB=qmf_b200/libqmf_b200_prof.so
+QMFB_SOLVE=classic timeout 300 python tools/exp_phases.py 11840,208,17800 > gpurun_out/r02_phases_classic_mma.log 2>&1
+cat gpurun_out/r02_phases_classic_mma.log

@@ -82,24 +82,33 @@ __global__ void kern(double* out, long long* cyc, int iters) {
   bool ok = true;
   long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
-    if (V == 0) ok = factor_diag_tile(tile[warp], w[warp], scr[warp], lane) && ok;
+    const double2 a = *reinterpret_cast<const double2*>(tile[warp] + tile_acc_off(lane));
+    if (V == 0) ok = factor_diag_tile(a.x, a.y, w[warp], scr[warp], lane) && ok;
+    if (V == 3) ok = factor_diag_tile_mma(a.x, a.y, w[warp], lane) && ok;
     if (V == 1) ok = factor_noinv(tile[warp], w[warp], lane) && ok;
     if (V == 2) ok = factor_smem(tile[warp], w[warp], scr[warp], lane) && ok;
     __syncwarp();
   }
   long long t1 = clock64();
   if (threadIdx.x == 0 && blockIdx.x == 0) cyc[V] = (t1 - t0) / iters;
-  out[threadIdx.x] = w[warp][lane] + ok;
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    out[V * 64 + lane] = w[0][lane] + (ok ? 0.0 : 1e9);
+    out[V * 64 + 32 + lane] = w[0][32 + lane];
+  }
 }
 
 int main() {
-  double* out; long long* cyc; cudaMalloc(&out, 4096); cudaMalloc(&cyc, 64);
+  double* out; long long* cyc; cudaMalloc(&out, 8192); cudaMalloc(&cyc, 64);
   for (int warps : {1, 8}) {
     kern<0><<<148, 32 * warps>>>(out, cyc, 200);
     kern<1><<<148, 32 * warps>>>(out, cyc, 200);
     kern<2><<<148, 32 * warps>>>(out, cyc, 200);
-    long long h[3]; cudaMemcpy(h, cyc, 24, cudaMemcpyDeviceToHost);
-    printf("warps/CTA=%d: shuffle+inverse %lld  shuffle no-inverse %lld  smem-broadcast+inverse %lld cycles/tile\n", warps, h[0], h[1], h[2]);
+    kern<3><<<148, 32 * warps>>>(out, cyc, 200);
+    long long h[4]; cudaMemcpy(h, cyc, 32, cudaMemcpyDeviceToHost);
+    double w[256]; cudaMemcpy(w, out, sizeof(w), cudaMemcpyDeviceToHost);
+    double d = 0, m = 0;
+    for (int i = 0; i < 64; ++i) { d = fmax(d, fabs(w[i] - w[192 + i])); m = fmax(m, fabs(w[i])); }
+    printf("warps/CTA=%d: smem-broadcast+inverse (product) %lld  shuffle no-inverse %lld  smem unrolled %lld  DMMA-broadcast+inverse %lld cycles/tile; max |W_mma - W_smem| = %.3e (max |W| %.3e)\n", warps, h[0], h[1], h[2], h[3], d, m);
   }
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
