@@ -506,19 +506,174 @@ def run_ours(args, cfg, workload):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """BASELINE configs[4]: WALS + all-user p@10 / AUC evaluation on the 10M x 1M x 1B power-law problem, one
+    process per GPU, every rank generating ONLY its own shard (qmf_b200.datagen.powerlaw_shard_torch).
+    --c5-scale s shrinks users, items and draws by s (1 GPU: 0.125)."""
+    import torch
+    import torch.distributed as dist
+    from qmf_b200 import capi
+    from qmf_b200.datagen import CONFIGS, powerlaw_shard_torch
+    from qmf_b200.wals_dist import ShardedWals
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    nu, ni, draws, k = CONFIGS["c5"]
+    sc = float(args.c5_scale)
+    nu, ni, draws = int(nu * sc), int(ni * sc), int(draws * sc)
+    t_gen = time.perf_counter()
+    prob = powerlaw_shard_torch(nu, ni, draws, seed=20240505, device=device, rank=rank, world=world)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    nnz = prob["nnz"]
+    sw = ShardedWals(nu, ni, k, prob["csr_user"], prob["csr_item"], device, rank, world, exchange=args.exchange,
+                     ranges=prob["ranges"])
+    g = torch.Generator(device=device).manual_seed(7)
+    Y0 = (torch.rand(ni, k, generator=g, device=device, dtype=torch.float64) * 0.02 - 0.01)
+    sw.set_factors(1, Y0)
+    del Y0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sw.epoch(ALPHA, LAMBDA)
+    barrier()
+    sw.check_error()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[{n: torch.cuda.Event(enable_timing=True) for n in ("gram0", "solve0", "solve1")} for _ in range(2)]
+          for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sw.launches
+    barrier()
+    t0.record()
+    loss = None
+    for s in range(args.steps):
+        loss = sw.epoch(ALPHA, LAMBDA, ev[s])
+    t1.record()
+    barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    sw.check_error()
+    loss_value = float(loss.item())
+    launches = sw.launches - launches0
+    solve_ms = [[e[h]["solve0"].elapsed_time(e[h]["solve1"]) for h in range(2)] for e in ev]
+    fl_local = sum(algorithmic_flops(sw.shard[s]["end"] - sw.shard[s]["begin"], sw.shard[s]["nnz"], k) for s in (0, 1))
+    solve_s = float(np.mean([sum(x) for x in solve_ms])) * 1e-3
+    stats = torch.tensor([fl_local, solve_s, float(sw.shard[0]["nnz"]), float(sw.shard[1]["nnz"])], dtype=torch.float64, device=device)
+    allst = [torch.zeros_like(stats) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allst, stats)
+    else:
+        allst = [stats]
+    allst = [x.tolist() for x in allst]
+    fl_total = sum(x[0] for x in allst)
+    achieved_tf = fl_total / max(x[1] for x in allst) * 1e-12   # whole job: all ranks' flops / slowest rank's kernel time
+
+    # ---- all-user evaluation: every rank scores ITS users against all items on its full replicas ----------
+    ub, ue = sw.shard[0]["begin"], sw.shard[0]["end"]
+    nT = ue - ub
+    tu = torch.arange(ub, ue, device=device, dtype=torch.int32)
+    lp = torch.arange(nT + 1, device=device, dtype=torch.int64)
+    li = prob["test_items"][ub:ue].contiguous()
+    cnt = torch.zeros(2 * nT, device=device, dtype=torch.int32)
+    psc = torch.zeros(nT, device=device, dtype=torch.float64)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    kp = sw.kp
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    capi.check(capi.lib.qmfb_eval_rank_dev(st, sw.F[0].data_ptr(), kp, sw.F[1].data_ptr(), kp, ni, k, None, tu.data_ptr(), nT,
+                                           lp.data_ptr(), li.data_ptr(), nT, 1, cnt.data_ptr(), psc.data_ptr()))
+    b.record()
+    barrier()
+    ems = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    eval_s = float(ems.item()) * 1e-3
+    t_host = time.perf_counter()
+    cnt_h = cnt.cpu().numpy()
+    lp_h = np.arange(nT + 1, dtype=np.int64)
+    sums = []
+    for name in ("auc", "p@10"):
+        out = np.empty(nT, dtype=np.float64)
+        capi.check(capi.lib.qmfb_rank_metrics(name.encode(), cnt_h, lp_h, nT, ni, 0, out))
+        sums.append(float(out.sum()))
+    t_host = time.perf_counter() - t_host
+    tot = torch.tensor(sums + [float(cnt_h.sum())], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tot)
+    auc, p10 = float(tot[0].item()) / nu, float(tot[1].item()) / nu
+    assert int(tot[2].item()) == nu * (ni - 1), "every (user, negative item) pair must land in exactly one bucket"
+    clocks = sampler.stop() if rank == 0 else None
+    eval_tf = 2.0 * nu * ni * k / eval_s * 1e-12
+    if rank == 0:
+        peak = fp64_peak_tflops() * world
+        line = {
+            "metric": "wals_nnz_per_s", "value": nnz / (ms_per_step * 1e-3), "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "s_per_epoch": ms_per_step * 1e-3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C5 power-law 10M x 1M, 1B draws, k=128 (scale %g)" % sc, "nusers": nu, "nitems": ni,
+                       "nnz": nnz, "draws": draws, "nfactors": k, "alpha": ALPHA, "lambda": LAMBDA,
+                       "parallelism": "rows x%d, each rank generates and holds only its shard" % world,
+                       "exchange": sw.exchange if world > 1 else "none", "max_item_len": prob["max_item_len"],
+                       "max_user_len": prob["max_user_len"], "l2": "inputs larger than the 126 MB L2; no flush"},
+            "loss": loss_value, "gpu_launches": launches, "clocks": clocks, "generate_s": t_gen,
+            "roofline": {"kernel": "wals_solve(_ws)_kernel<16> + long-row pre-pass (between the solve events)", "bound": "tensor",
+                         "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tf / peak, "traffic": None,
+                         "algorithmic_flops_per_epoch": fl_total,
+                         "per_rank": [{"flops": x[0], "solve_s": x[1], "user_nnz": x[2], "item_nnz": x[3]} for x in allst],
+                         "peak_source": "builder-measured FP64 DMMA peak x n_gpus (profiles/fp64_peak.json)"},
+            "eval": {"test_users": nu, "nitems": ni, "seconds": eval_s, "host_metric_seconds": t_host, "auc": auc, "p@10": p10,
+                     "tflops": eval_tf, "roofline": {"bound": "tensor", "achieved": eval_tf, "peak": peak, "unit": "TFLOP/s",
+                                                     "frac": eval_tf / peak, "algorithmic_flops": 2.0 * nu * ni * k},
+                     "note": "one held-out item per user from the popularity law; every rank scores its own users against all "
+                             "items on its replicas (qmfb_eval_rank_dev), metric sums allreduced"},
+            "cpu_baseline": None, "e2e": None,
+            "note": "the reference cannot run C5 (1 B-line text parse, ~80 GB of AoS signals, dense nT x ni score matrix): "
+                    "no CPU arm; SURVEY.md 8d",
+            "lib": os.path.relpath(capi.LIB_PATH, ROOT),
+        }
+        print(json.dumps(line), flush=True)
+    sw.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c1", "c3", "c4"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--c5-scale", type=float, default=1.0, help="c5 only: shrink users, items and draws by this factor")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bpr", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N > 1: how the solved shards reach the other ranks (p2p = peer stores fused into the solve kernel)")
     args = ap.parse_args()
+    if args.workload == "c5":
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference cannot run C5 (1 B-line text parse, ~80 GB of "
+                                  "AoS signals, dense score matrix; SURVEY.md 8d)"}), flush=True)
+            return
+        return run_c5(args)
     from qmf_b200.datagen import CONFIGS
     cfg = CONFIGS[args.workload]
     names = {"c1": "C1 uniform 10k x 5k, 500k nnz, k=30", "c3": "C3 MovieLens-20M-shaped 138k x 27k, 20M nnz, k=64",

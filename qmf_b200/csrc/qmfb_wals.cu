@@ -84,7 +84,6 @@ static std::atomic<int> g_solve_kernel{[] {
 // rows of the matrix the next solve gathers from (set by the engines right before the launch; 0 = unknown)
 static std::atomic<int64_t> g_gather_rows_hint{0};
 
-constexpr int kWsMaxMeanRow = 1024;  // mean signals per row below which a half-step counts as "short rows"
 
 // nnz_hint: number of signals of the rows being solved (-1: unknown)
 template <int NT>
@@ -108,22 +107,28 @@ static int launch_solve(cudaStream_t st, const SolveParams& prm, double* loss_su
     static const int grid_env = getenv("QMFB_GRID_CAP") ? atoi(getenv("QMFB_GRID_CAP")) : 0;  // measurement switch
     const int grid = int(std::min<int64_t>(grid_env > 0 ? std::min(grid_env, grid_cap) : grid_cap, prm.nrows));
     // extremely long rows at the head of `order` are summed by many CTAs ahead of the solve kernel
-    // (two empty launches when there is none); stream-ordered scratch, freed after the kernel
+    // (three near-empty launches when there is none); stream-ordered scratch, freed after the kernel
     constexpr int kLen = LongRow<NT>::kLen;
     double* long_buf = nullptr;
-    QMFB_CUDA(cudaMallocAsync(&long_buf, size_t(kLongMax) * (kLongParts + 1) * kLen * sizeof(double), st));
+    const size_t plan_doubles = (sizeof(LongPlan) + 7) / 8;
+    QMFB_CUDA(cudaMallocAsync(&long_buf, (size_t(kLongMaxSegs + kLongMaxRows) * kLen + plan_doubles) * sizeof(double), st));
     LongRowParams lp{prm.Y, prm.ldy, prm.row_ptr, prm.col, prm.val, prm.order, prm.nrows, prm.alpha, long_buf,
-                     long_buf + size_t(kLongMax) * kLongParts * kLen};
-    long_row_partial_kernel<NT><<<dim3(kLongParts, kLongMax), SM::NTHREADS, SM::kBytes, st>>>(lp);
-    long_row_reduce_kernel<NT><<<dim3((kLen + 255) / 256, kLongMax), 256, 0, st>>>(lp);
+                     long_buf + size_t(kLongMaxSegs) * kLen,
+                     reinterpret_cast<LongPlan*>(long_buf + size_t(kLongMaxSegs + kLongMaxRows) * kLen)};
+    long_row_plan_kernel<<<1, kLongMaxRows, 0, st>>>(lp);
+    long_row_partial_kernel<NT><<<grid_cap, SM::NTHREADS, SM::kBytes, st>>>(lp);
+    long_row_reduce_kernel<NT><<<dim3((kLen + 255) / 256, 32), 256, 0, st>>>(lp);
     SolveParams run = prm;
     static const bool no_long = getenv("QMFB_NO_LONG_ROWS") != nullptr;  // measurement switch: ignore the sums
     run.long_sum = no_long ? nullptr : lp.sum;
-    // Row bucketing by length (north_star): half-steps of SHORT rows (solve-latency bound: the Cholesky chain of
-    // a row is longer than its build) run the warp-specialised kernel - one CTA per SM, builders + two solver
-    // groups, three rows in flight; LONG rows (build bound) run two plain CTAs per SM.
-    // qmfb_wals_set_solve_kernel / QMFB_SOLVE=classic|ws override the choice (tests, measurements).
-    bool ws = NT == 16 && nnz_hint >= 0 && nnz_hint < int64_t(kWsMaxMeanRow) * prm.nrows;
+    run.long_plan = lp.plan;
+    // Two solve kernels: the plain one (two CTAs per SM, each alternating build and solve) and the warp-specialised
+    // one (one CTA per SM: builder warps + two solver groups, three rows in flight).  Measured on the user-shaped
+    // half of C4 (gpurun r02_variants.log): 24.75 ms plain vs 24.95 - 27.3 ms warp-specialised - its 4-warp solver
+    // groups are slower per row than the 8-warp solve and the build no longer hides them - so the plain kernel is the
+    // default for every row length; qmfb_wals_set_solve_kernel(2) / QMFB_SOLVE=ws selects the other (tests, measurements).
+    (void)nnz_hint;
+    bool ws = false;
     const int mode = g_solve_kernel.load();
     if (mode == 1) ws = false;
     if (mode == 2) ws = true;
@@ -600,7 +605,7 @@ static int wals_half_step_async(qmfb_wals* h, int side, double alpha, double lam
   if (rc) return rc;
   QMFB_CUDA(cudaEventRecord(h->ev[2], h->stream));
   // gram_partial, gram_reduce, [long_row_partial, long_row_reduce (k <= 128)], wals_solve, sum
-  h->launches += (h->nrows[side] > 0 && h->kp <= 128) ? 6 : 4;
+  h->launches += (h->nrows[side] > 0 && h->kp <= 128) ? 7 : 4;
   return QMFB_OK;
 }
 

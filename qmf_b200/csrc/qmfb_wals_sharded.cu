@@ -173,7 +173,7 @@ int half_step_async(qmfb_wals_sharded* h, int side, double alpha, double lambda,
                                            s.col[side], s.val[side], s.order[side], s.nrows[side], s.nnz[side], s.gram_packed, alpha, lambda,
                                            s.row_loss, s.loss_sum, s.scratch, peers, np)) return rc;
     if (d == 0) QMFB_CUDA(cudaEventRecord(h->tev[2], s.stream));
-    h->launches += 2 + ((s.nrows[side] > 0) ? (h->kp <= 128 ? 3 : 1) : 0);  // reduce, sum, [long partial, long reduce,] solve
+    h->launches += 2 + ((s.nrows[side] > 0) ? (h->kp <= 128 ? 4 : 1) : 0);  // reduce, sum, [long plan, long partial, long reduce,] solve
     QMFB_CUDA(cudaMemcpyAsync(h->err_host + size_t(slot * N + d) * 2, s.scratch, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
     // loss terms of this shard -> device 0's full array (global row order)
     if (s.nrows[side] > 0) {

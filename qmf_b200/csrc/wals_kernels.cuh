@@ -368,16 +368,35 @@ __global__ void gram_unpack_kernel(const double* __restrict__ packed, int k, dou
 }
 
 // ------------------------------------------------------------------------------------------
-// Extremely long rows (a blockbuster item): a row is normally built by ONE CTA, so a single row of
-// several hundred thousand entries would be the tail of its half-step (and of every rank's, multi-GPU).
-// The kLongMax longest rows (the head of `order`) that have >= kLongRow entries are therefore built
-// ahead of the solve kernel by kLongParts CTAs each - the Gram kernel's scheme on gathered, weighted
-// rows - and reduced in a fixed order; the solve kernel then starts such a row from
-// Gram + that sum and skips its own gather loop.  Rows below the threshold cost two empty launches.
+// Extremely long rows (blockbuster items of a power-law catalogue): a row is normally built by ONE
+// CTA, so a row of several hundred thousand entries would be the tail of its half-step (and of every
+// rank's, multi-GPU).  Every row at the head of `order` (longest first) with >= kLongRow entries is
+// therefore cut into segments - a work list of (row, segment) units, any number of rows up to the
+// buffer bounds below - that the persistent CTAs of long_row_partial_kernel build ahead of the solve
+// kernel (the Gram kernel's TMA scheme on gathered, weighted rows) and that long_row_reduce_kernel
+// sums in a fixed order; the solve kernel then starts such a row from Gram + that sum and skips its
+// own gather loop.  The segment length of a row is a function of ITS length only, so its sum (and with
+// it the factors and the loss) does not depend on how rows are sharded over GPUs.  The plan is made
+// on the device (no host synchronisation); without long rows the cost is three near-empty launches.
 // ------------------------------------------------------------------------------------------
-constexpr int kLongMax = 16;          // candidate rows: positions [0, kLongMax) of `order`
-constexpr int kLongParts = 64;        // CTAs per long row
-constexpr int64_t kLongRow = 32768;   // entries
+constexpr int kLongMaxRows = 512;      // candidate rows: positions [0, kLongMaxRows) of `order`
+constexpr int kLongMaxSegs = 2048;     // work units the partial buffer holds
+constexpr int kLongMaxParts = 256;     // segments per row
+constexpr int64_t kLongRow = 32768;    // entries from which a row counts as extremely long
+constexpr int64_t kLongSegMin = 4096;  // entries per segment, at least
+
+__host__ __device__ inline int64_t long_seg_len(int64_t len) {
+  int64_t s = (len + kLongMaxParts - 1) / kLongMaxParts;
+  s = (s + kChunk - 1) / kChunk * kChunk;
+  return s < kLongSegMin ? kLongSegMin : s;
+}
+
+struct LongPlan {  // device memory, written by long_row_plan_kernel
+  int nlong;       // rows order[0 .. nlong) are prebuilt
+  int nseg;        // work units
+  int pad[2];
+  int seg_begin[kLongMaxRows + 1];  // first work unit of row position r
+};
 
 template <int NT>
 struct LongRow {
@@ -393,18 +412,47 @@ struct LongRowParams {
   const int32_t* order;
   int nrows;
   double alpha;
-  double* partial;  // [kLongMax][kLongParts][kLen]
-  double* sum;      // [kLongMax][kLen]
+  double* partial;  // [kLongMaxSegs][kLen]
+  double* sum;      // [kLongMaxRows][kLen]
+  LongPlan* plan;
 };
+
+// one CTA of kLongMaxRows threads: the longest prefix of `order` whose rows are all long and whose
+// segments fit the buffer
+__global__ void __launch_bounds__(kLongMaxRows) long_row_plan_kernel(const LongRowParams prm) {
+  __shared__ int cum[kLongMaxRows];
+  const int t = threadIdx.x;
+  int parts = kLongMaxSegs + 1;  // "not long": ends the prefix
+  if (t < prm.nrows) {
+    const int row = prm.order[t];
+    const int64_t len = prm.row_ptr[row + 1] - prm.row_ptr[row];
+    if (len >= kLongRow) parts = int((len + long_seg_len(len) - 1) / long_seg_len(len));
+  }
+  cum[t] = parts;
+  __syncthreads();
+  for (int o = 1; o < kLongMaxRows; o <<= 1) {  // inclusive scan (values stay < 2^31: 512 * 2049)
+    const int v = t >= o ? cum[t - o] : 0;
+    __syncthreads();
+    cum[t] += v;
+    __syncthreads();
+  }
+  const bool ok = cum[t] <= kLongMaxSegs;
+  const int nlong = __syncthreads_count(ok);  // cum is increasing: the ok positions are a prefix
+  if (ok) prm.plan->seg_begin[t] = cum[t] - parts;
+  if (t == nlong - 1) prm.plan->seg_begin[nlong] = cum[t];
+  if (t == 0) {
+    prm.plan->nlong = nlong;
+    prm.plan->nseg = nlong > 0 ? cum[nlong - 1] : 0;
+    if (nlong == 0) prm.plan->seg_begin[0] = 0;
+  }
+}
 
 template <int NT>
 __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) long_row_partial_kernel(const LongRowParams prm) {
   using SM = WalsSmem<NT>;
-  const int r = blockIdx.y;
-  if (r >= prm.nrows) return;
-  const int row = prm.order[r];
-  const int64_t p0 = prm.row_ptr[row], p1 = prm.row_ptr[row + 1];
-  if (p1 - p0 < kLongRow) return;
+  const int nseg = prm.plan->nseg;
+  if (int(blockIdx.x) >= nseg) return;
+  const int nlong = prm.plan->nlong;
   extern __shared__ __align__(128) unsigned char smem[];
   double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
   double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
@@ -419,83 +467,98 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) long_row_partial_kerne
     mbar_fence_init();
   }
   __syncthreads();
-  const int64_t n = p1 - p0;
-  const int64_t s0 = p0 + n * blockIdx.x / gridDim.x, s1 = p0 + n * (blockIdx.x + 1) / gridDim.x;
-  const int nch = int((s1 - s0 + kChunk - 1) / kChunk);
-  double csum = 0.0;
-
-  auto issue = [&](int c) {  // warp 0 only: one TMA bulk copy per gathered row
-    const uint32_t st = c % kStages;
-    if (c >= kStages) mbar_wait(&empty[st], ((c / kStages) & 1u) ^ 1u);
-    const int64_t p = s0 + int64_t(c) * kChunk + lane;
-    const bool valid = lane < kChunk && p < s1;
-    const double v = valid ? prm.val[p] : 0.0;
-    const int32_t src = valid ? prm.col[p] : 0;
-    if (lane < kChunk) {
-      const double wb = valid ? 1.0 + prm.alpha * v : 0.0;        // WALSEngine.cpp:280
-      wts[st * 2 * kChunk + lane] = valid ? prm.alpha * v : 0.0;  // WALSEngine.cpp:282
-      wts[st * 2 * kChunk + kChunk + lane] = wb;
-      csum += wb;
+  uint32_t cbase = 0;  // chunks this CTA has streamed so far: the ring's stage / phase run on across work units
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    // work unit -> (row position r, segment j): last r with seg_begin[r] <= seg
+    int lo = 0, hi = nlong - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (prm.plan->seg_begin[mid] <= seg) lo = mid; else hi = mid - 1;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive_expect_tx(&full[st], uint32_t(kChunk) * SM::KP * 8);
-    __syncwarp();
-    if (lane < kChunk) bulk_g2s(stagebuf + (size_t(st) * kChunk + lane) * SM::LD, prm.Y + int64_t(src) * prm.ldy, SM::KP * 8, &full[st]);
-  };
+    const int r = lo, j = seg - prm.plan->seg_begin[r];
+    const int row = prm.order[r];
+    const int64_t p0 = prm.row_ptr[row], p1 = prm.row_ptr[row + 1];
+    const int64_t sl = long_seg_len(p1 - p0);
+    const int64_t s0 = p0 + int64_t(j) * sl, s1 = s0 + sl < p1 ? s0 + sl : p1;
+    const int nch = int((s1 - s0 + kChunk - 1) / kChunk);
+    double csum = 0.0;
 
-  double acc[NT + 3][2];
+    auto issue = [&](int c) {  // warp 0 only: one TMA bulk copy per gathered row
+      const uint32_t gc = cbase + uint32_t(c);
+      const uint32_t st = gc % kStages;
+      if (gc >= kStages) mbar_wait(&empty[st], ((gc / kStages) & 1u) ^ 1u);
+      const int64_t p = s0 + int64_t(c) * kChunk + lane;
+      const bool valid = lane < kChunk && p < s1;
+      const double v = valid ? prm.val[p] : 0.0;
+      const int32_t src = valid ? prm.col[p] : 0;
+      if (lane < kChunk) {
+        const double wb = valid ? 1.0 + prm.alpha * v : 0.0;        // WALSEngine.cpp:280
+        wts[st * 2 * kChunk + lane] = valid ? prm.alpha * v : 0.0;  // WALSEngine.cpp:282
+        wts[st * 2 * kChunk + kChunk + lane] = wb;
+        csum += wb;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(&full[st], uint32_t(kChunk) * SM::KP * 8);
+      __syncwarp();
+      if (lane < kChunk) bulk_g2s(stagebuf + (size_t(st) * kChunk + lane) * SM::LD, prm.Y + int64_t(src) * prm.ldy, SM::KP * 8, &full[st]);
+    };
+
+    double acc[NT + 3][2];
 #pragma unroll
-  for (int t = 0; t < NT + 3; ++t) acc[t][0] = acc[t][1] = 0.0;
-  double bacc = 0.0;
-  if (warp == 0) {
-    for (int c = 0; c < nch && c < kStages - 1; ++c) issue(c);
-  }
-  for (int c = 0; c < nch; ++c) {
-    const uint32_t st = c % kStages;
-    if (warp == 0 && c + kStages - 1 < nch) issue(c + kStages - 1);
-    mbar_wait(&full[st], (c / kStages) & 1u);
-    const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
-    const double* w8 = wts + st * 2 * kChunk;
-    {
-      const double* pb = sb + (lane >> 4) * SM::LD + warp * 16 + (lane & 15);
-      const double* pw = w8 + kChunk + (lane >> 4);
-#pragma unroll
-      for (int j = 0; j < kChunk / 2; ++j) bacc = fma(pw[2 * j], pb[2 * j * SM::LD], bacc);
+    for (int t = 0; t < NT + 3; ++t) acc[t][0] = acc[t][1] = 0.0;
+    double bacc = 0.0;
+    if (warp == 0) {
+      for (int c = 0; c < nch && c < kStages - 1; ++c) issue(c);
     }
-    chunk_mma_dispatch<NT, 0, false>(warp, acc, sb, w8, lane);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
-  }
-  double* out = prm.partial + (size_t(r) * kLongParts + blockIdx.x) * LongRow<NT>::kLen;
+    for (int c = 0; c < nch; ++c) {
+      const uint32_t gc = cbase + uint32_t(c);
+      const uint32_t st = gc % kStages;
+      if (warp == 0 && c + kStages - 1 < nch) issue(c + kStages - 1);
+      mbar_wait(&full[st], (gc / kStages) & 1u);
+      const double* sb = stagebuf + size_t(st) * kChunk * SM::LD;
+      const double* w8 = wts + st * 2 * kChunk;
+      {
+        const double* pb = sb + (lane >> 4) * SM::LD + warp * 16 + (lane & 15);
+        const double* pw = w8 + kChunk + (lane >> 4);
 #pragma unroll
-  for (int t = 0; t <= NT; ++t) {
-    int I, J;
-    acc_tile<NT>(warp, t, I, J);
-    *reinterpret_cast<double2*>(out + size_t(SM::gidx(I, J)) * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
-  }
-  bacc += __shfl_xor_sync(0xffffffffu, bacc, 16);
-  if (lane < 16) out[SM::NTILE_A * 64 + warp * 16 + lane] = bacc;
-  if (warp == 0) {
+        for (int jj = 0; jj < kChunk / 2; ++jj) bacc = fma(pw[2 * jj], pb[2 * jj * SM::LD], bacc);
+      }
+      chunk_mma_dispatch<NT, 0, false>(warp, acc, sb, w8, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    cbase += uint32_t(nch);
+    double* out = prm.partial + size_t(seg) * LongRow<NT>::kLen;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-    if (lane == 0) out[SM::NTILE_A * 64 + SM::KP] = csum;
+    for (int t = 0; t <= NT; ++t) {
+      int I, J;
+      acc_tile<NT>(warp, t, I, J);
+      *reinterpret_cast<double2*>(out + size_t(SM::gidx(I, J)) * 64 + lane * 2) = make_double2(acc[t][0], acc[t][1]);
+    }
+    bacc += __shfl_xor_sync(0xffffffffu, bacc, 16);
+    if (lane < 16) out[SM::NTILE_A * 64 + warp * 16 + lane] = bacc;
+    if (warp == 0) {
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+      if (lane == 0) out[SM::NTILE_A * 64 + SM::KP] = csum;
+    }
   }
 }
 
-// sum[r][t] = sum over the kLongParts partials of long row r, fixed order (deterministic)
+// sum[r][t] = sum over the segments of long row r, fixed order (deterministic)
 template <int NT>
 __global__ void long_row_reduce_kernel(const LongRowParams prm) {
-  const int r = blockIdx.y;
-  if (r >= prm.nrows) return;
-  const int row = prm.order[r];
-  if (prm.row_ptr[row + 1] - prm.row_ptr[row] < kLongRow) return;
+  const int nlong = prm.plan->nlong;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   constexpr int kLen = LongRow<NT>::kLen;
   if (t >= kLen) return;
-  const double* p = prm.partial + size_t(r) * kLongParts * kLen + t;
-  double s = 0.0;
-  for (int b = 0; b < kLongParts; ++b) s += p[size_t(b) * kLen];
-  prm.sum[size_t(r) * kLen + t] = s;
+  for (int r = blockIdx.y; r < nlong; r += gridDim.y) {
+    const int b0 = prm.plan->seg_begin[r], b1 = prm.plan->seg_begin[r + 1];
+    const double* p = prm.partial + t;
+    double s = 0.0;
+    for (int b = b0; b < b1; ++b) s += p[size_t(b) * kLen];
+    prm.sum[size_t(r) * kLen + t] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -524,7 +587,8 @@ struct SolveParams {
   // (same ldx / row_offset), instead of a separate collective after the kernel.
   int npeers;
   double* peerX[kMaxPeers];
-  const double* long_sum;  // [kLongMax][LongRow<NT>::kLen] prebuilt sums of the extremely long rows, or nullptr
+  const double* long_sum;  // [kLongMaxRows][LongRow<NT>::kLen] prebuilt sums of the extremely long rows, or nullptr
+  const LongPlan* long_plan;  // which rows those are (device memory; read when long_sum != nullptr)
   // 1: gather the factor rows with TMA bulk copies (one 8 KP-byte cp.async.bulk per row, issued by 16 lanes)
   // instead of 16-byte cp.async (32 per lane and chunk).  Cheap to issue, but the TMA engine's outstanding-request
   // window starves the loop when the gathered matrix is DRAM resident (profiles/r01_solve_v1_*): the launcher
@@ -924,7 +988,7 @@ __device__ __forceinline__ void solve_bars_init(double* fscratch) {
 }
 
 template <int NT, int NW, int TU, bool NAMED>
-__device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* bcopy, double* xvec, double* rvec, double* fscratch,
+__device__ __noinline__ bool solve_row_impl_decoupled(double* tiles, double* wt, double* bcopy, double* xvec, double* rvec, double* fscratch,
                                             int warp, int lane, int tid, int bar_id) {
   using SM = SolveDims<NT, NW>;
   static_assert(NW * 32 >= NT * 8, "one thread per unknown in the back substitution");
@@ -1129,6 +1193,178 @@ __device__ __noinline__ bool solve_row_impl(double* tiles, double* wt, double* b
 
 // SM is the shared-memory layout (WalsSmem<NT>: tiles in shared memory; WalsSmemBig<NT>, k > 128:
 // GT = true and the tiles live in the CTA's L2-resident global workspace `gtiles`): the whole CTA solves.
+// The same solve with BLOCK barriers: every warp of the group meets twice per panel step (W_I ready / panel row
+// complete); warp 0 takes the next diagonal tile from its DMMA accumulators straight into the factor (look-ahead)
+// while the others sweep the trailing tiles.  The measured round-1/2 default.
+template <int NT, int NW, int TU, bool NAMED>
+__device__ __noinline__ bool solve_row_impl_blocked(double* tiles, double* wt, double* bcopy, double* xvec, double* rvec, double* fscratch,
+                                            int warp, int lane, int tid, int bar_id) {
+  using SM = SolveDims<NT, NW>;
+  static_assert(NW * 32 >= NT * 8, "one thread per unknown in the back substitution");
+  const int fo = tile_frag_off(lane);                        // operand-fragment offset inside a tile
+  const int fw = (lane >> 2) * 8 + ((lane & 3) ^ tile_sw(lane >> 2));  // same for the transposed W tiles; k+4 half at fw ^ 4
+  const int co = tile_acc_off(lane);                         // accumulator-fragment offset
+  QMFB_T(tp1);
+  // keep a copy of b (column 0 of the b tiles) for the loss before the factorisation overwrites it with z
+  if (tid < SM::KP) bcopy[tid] = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
+  // ---- blocked Cholesky, panel width 8; forward substitution rides along in column NT ------
+  bool ok = true;
+  QMFB_T(tp2);
+  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 1, tp1, tp2);
+  if (warp == 0) {
+    const double2 a = *reinterpret_cast<const double2*>(tiles + size_t(SM::tidx(0, 0)) * 64 + co);
+    ok = factor_tile(a.x, a.y, wt, fscratch + 8, lane);
+  }
+  QMFB_T(tp3);
+  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 2, tp2, tp3);
+  for (int I = 0; I < NT; ++I) {
+    QMFB_T(ts0);
+    group_sync<NAMED>(bar_id, NW * 32);  // W_I ready, row I of tiles final up to panel I-1
+    QMFB_T(ts1);
+    QMFB_ACC_IF(tid == 0 && bar_id <= 1, 4, ts0, ts1);
+    // (b) panel: U[I][J] = inv(U_II)^T * A[I][J]  for J = I+1 .. NT
+    {
+      const double w0 = wt[I * 64 + fw], w1 = wt[I * 64 + (fw ^ 4)];
+      for (int J = I + 1 + warp; J <= NT; J += SM::NWARPS) {
+        double* t = tiles + size_t(SM::tidx(I, J)) * 64;
+        double c[2] = {0.0, 0.0};
+        dmma(c, w0, t[fo]);
+        dmma(c, w1, t[fo + 32]);
+        __syncwarp();
+        *reinterpret_cast<double2*>(t + co) = make_double2(c[0], c[1]);
+      }
+    }
+    QMFB_T(ts2);
+    QMFB_ACC_IF(tid == 0 && bar_id <= 1, 3, ts1, ts2);
+    if (I == NT - 1) break;
+    group_sync<NAMED>(bar_id, NW * 32);
+    QMFB_T(ts3);
+    QMFB_ACC_IF(tid == 0 && bar_id <= 1, 5, ts2, ts3);
+    // (c) trailing update: A[J1][J2] -= U[I][J1]^T U[I][J2], I < J1 <= J2 <= NT, J1 < NT.
+    //     One warp updates the next diagonal tile first and factors it right away (look-ahead)
+    //     while the other warps sweep the rest (kTU tiles in flight each).
+    const int tstart = SM::tidx(I + 1, I + 1);
+    const double* urow = tiles + size_t(SM::tidx(I, I)) * 64;  // tile (I, J) = urow + (J - I) * 64
+    constexpr int dwarp = 0;
+    const int nw = SM::NWARPS > 1 ? SM::NWARPS - 1 : 1;
+    const int wslot = SM::NWARPS > 1 ? warp - 1 : 0;
+    if (SM::NWARPS == 1 || warp == dwarp) {
+      double* t = tiles + size_t(tstart) * 64;
+      const double* u = urow + 64;
+      double2 cv = *reinterpret_cast<double2*>(t + co);
+      double c[2] = {cv.x, cv.y};
+      const double u0 = u[fo], u1 = u[fo + 32];
+      dmma(c, -u0, u0);
+      dmma(c, -u1, u1);
+      QMFB_T(tf0);  // the updated tile goes to the factor in registers (same fragment layout); U_II itself is never read again
+      ok = factor_tile(c[0], c[1], wt + (I + 1) * 64, fscratch + 8, lane) && ok;
+      QMFB_T(tf1);
+      QMFB_ACC_IF(tid == 0 && bar_id <= 1, 2, tf0, tf1);
+      QMFB_ACC_IF(tid == 0 && bar_id <= 1, 6, ts3, tf0);
+    }
+#ifdef QMFB_PROFILE_PHASES
+    if ((g_debug_flags & 1) == 0)
+#endif
+    if (SM::NWARPS == 1 || warp != dwarp) {
+      // flat enumeration of the trailing tiles (contiguous in storage); (J1, J2) decoded incrementally
+      int J1 = I + 1, off = 1 + wslot;  // position `off` inside row J1 (row J1 has NT - J1 + 1 tiles)
+      for (int e = tstart + 1 + wslot; e < SM::NTILE; e += TU * nw) {
+        // straight-line body: out-of-range slots of the last sweep recompute a valid tile and skip the store
+        double c[TU][2], ua[TU][2], ub[TU][2];
+#pragma unroll
+        for (int q = 0; q < TU; ++q) {
+          const int ti = e + q * nw;
+          const bool v = ti < SM::NTILE;
+          if (v) {
+            while (off >= NT - J1 + 1) {
+              off -= NT - J1 + 1;
+              ++J1;
+            }
+          }
+          const double* ta = urow + (v ? J1 - I : 1) * 64;
+          const double* tb = urow + (v ? J1 + off - I : 1) * 64;
+          const double2 cv = *reinterpret_cast<const double2*>(tiles + size_t(v ? ti : tstart) * 64 + co);
+          c[q][0] = cv.x; c[q][1] = cv.y;
+          ua[q][0] = -ta[fo]; ua[q][1] = -ta[fo + 32];
+          ub[q][0] = tb[fo]; ub[q][1] = tb[fo + 32];
+          off += nw;
+        }
+#pragma unroll
+        for (int q = 0; q < TU; ++q) {
+          dmma(c[q], ua[q][0], ub[q][0]);
+          dmma(c[q], ua[q][1], ub[q][1]);
+        }
+#pragma unroll
+        for (int q = 0; q < TU; ++q) {
+          const int ti = e + q * nw;
+          if (ti < SM::NTILE) *reinterpret_cast<double2*>(tiles + size_t(ti) * 64 + co) = make_double2(c[q][0], c[q][1]);
+        }
+      }
+    }
+  }
+  QMFB_T(tp4);
+  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 7, tp3, tp4);
+
+  // ---- back substitution U x = z: thread t < KP keeps r_t in a register; per block step one
+  //      8x8 mat-vec by inv(U_JJ) and one rank-8 update of the rows above -----------------------
+  //      ONE block barrier per step: the eight threads of block J live in one warp, so they exchange
+  //      their finished r_J through shared memory under a __syncwarp and go straight on to x_J.
+  group_sync<NAMED>(bar_id, NW * 32);
+  double r = 0.0;
+  if (tid < SM::KP) r = tiles[size_t(SM::tidx(tid >> 3, NT)) * 64 + (tid & 7) * 8 + tile_sw(tid & 7)];
+  for (int J = NT - 1; J >= 0; --J) {
+    const bool mine = (tid >> 3) == J;
+    if (mine) rvec[tid & 7] = r;
+    __syncwarp();
+    if (mine) {  // x_J = W_J * r_J
+      const double* w = wt + J * 64;  // transposed: inv(U_JJ)[row][c] = w(c, row)
+      const int row = tid & 7;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        s0 += w[c * 8 + (row ^ tile_sw(c))] * rvec[c];
+        s1 += w[(c + 1) * 8 + (row ^ tile_sw(c + 1))] * rvec[c + 1];
+      }
+      xvec[tid] = s0 + s1;
+    }
+    if (J == 0) break;
+    group_sync<NAMED>(bar_id, NW * 32);  // x_J visible; also orders this step's rvec reads before the next step's writes
+    if (tid < 8 * J) {  // r_t -= U[t][8J .. 8J+7] . x_J
+      const double* u = tiles + size_t(SM::tidx(tid >> 3, J)) * 64 + (tid & 7) * 8;
+      const double* x = xvec + 8 * J;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        const int cr = (c + 2 * ((tid >> 1) & 3)) & 7;  // rotate the start pair by row/2: 8 rows -> 8 bank groups
+        const double2 uv = *reinterpret_cast<const double2*>(u + (cr ^ tile_sw(tid & 7)));
+        s0 += uv.x * x[cr];
+        s1 += uv.y * x[cr + 1];
+      }
+      r -= s0 + s1;
+    }
+  }
+  QMFB_T(tp5);
+  QMFB_ACC_IF(tid == 0 && bar_id <= 1, 8, tp4, tp5);
+  return ok;
+}
+
+
+// SM is the shared-memory layout (WalsSmem<NT>: tiles in shared memory; WalsSmemBig<NT>, k > 128:
+// GT = true and the tiles live in the CTA's L2-resident global workspace `gtiles`): the whole CTA solves.
+
+#ifndef QMFB_DECOUPLED
+#define QMFB_DECOUPLED 0   // 1: solve_row_impl_decoupled (chain warp + sweepers on mbarriers), 0: solve_row_impl_blocked
+#endif
+template <int NT, int NW, int TU, bool NAMED>
+__device__ __forceinline__ bool solve_row_impl(double* tiles, double* wt, double* bcopy, double* xvec, double* rvec, double* fscratch,
+                                               int warp, int lane, int tid, int bar_id) {
+#if QMFB_DECOUPLED
+  return solve_row_impl_decoupled<NT, NW, TU, NAMED>(tiles, wt, bcopy, xvec, rvec, fscratch, warp, lane, tid, bar_id);
+#else
+  return solve_row_impl_blocked<NT, NW, TU, NAMED>(tiles, wt, bcopy, xvec, rvec, fscratch, warp, lane, tid, bar_id);
+#endif
+}
+
 template <class SM, bool GT>
 __device__ __forceinline__ bool solve_row(unsigned char* smem, double* gtiles) {
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -1177,6 +1413,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
   volatile RowSlot* slots = reinterpret_cast<volatile RowSlot*>(smem + SM::kOffRow);
   const int G = gridDim.x, bid = blockIdx.x;
   auto slot_of = [&](int i) { return i * G + ((i & 1) ? (G - 1 - bid) : bid); };
+  const int nlong = prm.long_sum != nullptr ? __ldg(&prm.long_plan->nlong) : 0;  // rows order[0 .. nlong) are prebuilt
   if (tid == 0) {
     const int s0 = slot_of(0);
     const int r0 = s0 < prm.nrows ? prm.order[s0] : -1;
@@ -1200,7 +1437,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
     QMFB_T(tp0);
     // an extremely long row at the head of `order` was summed ahead of this kernel: no gather loop
     const int opos = slot_of(it);
-    const bool is_long = prm.long_sum != nullptr && opos < kLongMax && (cs->p1 - cs->p0) >= kLongRow;
+    const bool is_long = opos < nlong;
     const int64_t bp1 = is_long ? cs->p0 : cs->p1;
     build_row<SM, false>(smem, prm.Y, prm.ldy, prm.col, prm.val, prm.gram, prm.alpha, prm.lambda, prm.k, cs->p0, bp1, cs->base,
                          is_long ? prm.long_sum + size_t(opos) * LongRow<NT>::kLen : nullptr, tiles, bhalf, nullptr, 0u, false,
@@ -1288,6 +1525,7 @@ __global__ void __launch_bounds__(WalsSmemWs<NT>::NTHREADS, 1) wals_solve_ws_ker
   __syncthreads();
   const int G = gridDim.x, bid = blockIdx.x;
   auto slot_of = [&](int i) { return i * G + ((i & 1) ? (G - 1 - bid) : bid); };
+  const int nlong = prm.long_sum != nullptr ? __ldg(&prm.long_plan->nlong) : 0;  // rows order[0 .. nlong) are prebuilt
 
   if (warp < NB) {
     // ================= builders: rows it = 0, 1, 2, ... of this CTA's serpentine schedule =================
@@ -1316,7 +1554,7 @@ __global__ void __launch_bounds__(WalsSmemWs<NT>::NTHREADS, 1) wals_solve_ws_ker
         if (sn < prm.nrows) nrow = __ldg(prm.order + sn);
       }
       const int opos = slot_of(it);
-      const bool is_long = prm.long_sum != nullptr && opos < kLongMax && (cs->p1 - cs->p0) >= kLongRow;
+      const bool is_long = opos < nlong;
       const int64_t bp1 = is_long ? cs->p0 : cs->p1;
       const int b = it & 1;
       QMFB_T(tb0);

@@ -96,7 +96,7 @@ class CudaKernels:
     def ipc_free(self, ptr):
         self.lib.qmfb_ipc_free(C.c_void_p(ptr))
 
-    launches_per_half_step = 6  # gram_partial, gram_reduce, long_row_partial, long_row_reduce, wals_solve, sum
+    launches_per_half_step = 7  # gram_partial, gram_reduce, long_row_plan, long_row_partial, long_row_reduce, wals_solve, sum
 
 
 class _DeviceBuffer:
@@ -111,7 +111,12 @@ class ShardedWals:
     """State of one rank.  `csr[side]` = (row_ptr int64 [n+1], col int32 [nnz], val f64 [nnz]) of
     the FULL problem for that orientation, on `device`; the rank keeps only its slice."""
 
-    def __init__(self, nusers, nitems, k, csr_user, csr_item, device, rank=0, world=1, kernels=None, exchange="auto"):
+    def __init__(self, nusers, nitems, k, csr_user, csr_item, device, rank=0, world=1, kernels=None, exchange="auto",
+                 ranges=None):
+        """ranges=None: csr_* hold the FULL problem and are cut here into nnz-balanced contiguous row ranges.
+        ranges=(user_ranges, item_ranges), each a list of `world` (begin, end): csr_* are ALREADY this rank's
+        rows only (row_ptr local, starting at 0) - the form for problems no single GPU should materialise
+        (C5: qmf_b200.datagen.powerlaw_shard_torch)."""
         self.n = (int(nusers), int(nitems))
         self.k = int(k)
         self.rank, self.world = rank, world
@@ -131,21 +136,34 @@ class ShardedWals:
             self.F = [torch.zeros(self.n[s], self.kp, dtype=torch.float64, device=device) for s in (0, 1)]
         self.ranges, self.shard = [], []
         for side, (rp, col, val) in enumerate((csr_user, csr_item)):
-            ranges = balanced_row_ranges(rp, world)
-            b, e = ranges[rank]
-            p0, p1 = int(rp[b]), int(rp[e])
-            lrp = (rp[b:e + 1] - rp[b]).contiguous()
-            lcol = col[p0:p1].contiguous() if p1 > p0 else torch.zeros(1, dtype=torch.int32, device=device)
-            lval = val[p0:p1].contiguous() if p1 > p0 else torch.zeros(1, dtype=torch.float64, device=device)
+            if ranges is not None:
+                rr = [(int(b), int(e)) for b, e in ranges[side]]
+                b, e = rr[rank]
+                assert rp.numel() == e - b + 1, "local row_ptr does not match this rank's range"
+                lrp, lcol, lval, p0, p1 = rp.contiguous(), col.contiguous(), val.contiguous(), 0, int(rp[-1])
+                if p1 == 0:
+                    lcol = torch.zeros(1, dtype=torch.int32, device=device)
+                    lval = torch.zeros(1, dtype=torch.float64, device=device)
+            else:
+                rr = balanced_row_ranges(rp, world)
+                b, e = rr[rank]
+                p0, p1 = int(rp[b]), int(rp[e])
+                lrp = (rp[b:e + 1] - rp[b]).contiguous()
+                lcol = col[p0:p1].contiguous() if p1 > p0 else torch.zeros(1, dtype=torch.int32, device=device)
+                lval = val[p0:p1].contiguous() if p1 > p0 else torch.zeros(1, dtype=torch.float64, device=device)
             lens = lrp[1:] - lrp[:-1]
             order = torch.argsort(lens, descending=True, stable=True).to(torch.int32).contiguous()
-            self.ranges.append(ranges)
+            self.ranges.append(rr)
             self.shard.append(dict(begin=b, end=e, row_ptr=lrp, col=lcol, val=lval, order=order, nnz=p1 - p0))
         self.gram_packed = torch.zeros(self.kern.gram_packed_len(self.k), dtype=torch.float64, device=device)
         self.gram_ws = torch.empty(self.kern.gram_workspace_len(self.k), dtype=torch.float64, device=device)
         self.row_loss = torch.zeros(max(max(s["end"] - s["begin"] for s in self.shard), 1), dtype=torch.float64,
                                     device=device)
-        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
+        # [0] = loss sum of the last half-step (written by the kernel), [1] = number of half-steps, on ANY rank and
+        # since the last check_error(), in which a pivot was not positive: both travel in the one allreduce
+        # that follows a half-step, so every rank sees the same flag and raises together
+        self.loss_err = torch.zeros(2, dtype=torch.float64, device=device)
+        self.loss_sum = self.loss_err[:1]
         self.scratch = torch.zeros(2, dtype=torch.int32, device=device)
         self.launches = 0
         self.timing = None  # optional dict of torch.cuda.Event pairs filled by half_step(record=True)
@@ -243,6 +261,8 @@ class ShardedWals:
         if events is not None:
             events["solve1"].record()
         self.launches += self.kern.launches_per_half_step
+        # the launcher clears scratch (the NOT_SPD flag) at the start of every solve: fold it into the sticky count
+        self.loss_err[1:2] += self.scratch[1:2]
         if self.world > 1:
             if self.exchange != "p2p":
                 for r, (b, e) in enumerate(self.ranges[side]):
@@ -250,7 +270,7 @@ class ShardedWals:
                         dist.broadcast(self.F[side][b:e], src=r)
             # also the cross-rank ordering point of the p2p exchange: it completes on a rank only after every
             # rank's solve kernel (and with it that rank's peer stores) has completed
-            dist.all_reduce(self.loss_sum)
+            dist.all_reduce(self.loss_err)
         return self.loss_sum
 
     def epoch(self, alpha, lam, events=None):
@@ -284,5 +304,8 @@ class ShardedWals:
         return loss
 
     def check_error(self):
-        if int(self.scratch[1].item()) != 0:
+        """Raises on EVERY rank if any rank hit a non-positive pivot in any half-step since the last call."""
+        bad = float(self.loss_err[1].item()) != 0.0
+        self.loss_err[1:2].zero_()
+        if bad:
             raise RuntimeError("normal equations not positive definite (reference: dsysv failed, qmf/Matrix.cpp:94)")

@@ -275,6 +275,60 @@ def test_extremely_long_row_is_built_by_many_ctas(oracle_lib):
     assert abs(lu - lu_o) <= LOSS_TOL * abs(lu_o) and abs(li - li_o) <= LOSS_TOL * abs(li_o)
 
 
+@pytest.mark.parametrize("k,mode", [(128, 1), (128, 2), (30, 0)])
+def test_power_law_items_many_long_rows(oracle_lib, k, mode):
+    """Zipf-like item popularity: a dozen items above kLongRow with very different lengths (one of them
+    above kLongMaxParts * kLongSegMin entries, so its segments are longer than the minimum) go through the
+    (row, segment) work list; sampled rows are checked against the oracle's row update and the loss
+    against the per-row terms.  Both solve kernels."""
+    from qmf_b200 import WalsEngineHandle, capi, csr_from_coo
+    rng = np.random.default_rng(2024)
+    nu, ni = 1_300_000, 400
+    lens = np.maximum((1_200_000 / np.arange(1, ni + 1) ** 1.0).astype(np.int64), 40)
+    assert (lens >= 32768).sum() >= 12 and lens[0] > 256 * 4096
+    us = [rng.choice(nu, size=int(n), replace=False) for n in lens]
+    u = np.concatenate(us).astype(np.int64)
+    i = np.repeat(np.arange(ni), lens).astype(np.int64)
+    v = rng.integers(1, 6, size=len(u)).astype(np.float64)
+    uids, urp, uci, uv = csr_from_coo(u, i, v)
+    iids, irp, ici, iv = csr_from_coo(i, u, v)
+    NU, NI = len(uids), len(iids)
+    alpha, lam = 40.0, 0.05
+    try:
+        capi.check(capi.lib.qmfb_wals_set_solve_kernel(mode))
+        h = WalsEngineHandle(NU, NI, k)
+        h.set_csr(0, urp, uci, uv)
+        h.set_csr(1, irp, ici, iv)
+        Y0 = init_factors(NI, k, seed=5)
+        h.set_factors(1, Y0)
+        h.half_step(0, alpha, lam)
+        X = h.get_factors(0)
+        li = h.half_step(1, alpha, lam)
+        Y = h.get_factors(1)
+        h.close()
+    finally:
+        capi.check(capi.lib.qmfb_wals_set_solve_kernel(0))
+    # item rows from the GPU's own user factors: normal equations in numpy (float64, same formulas as
+    # WALSEngine.cpp:277-304), every long row + a few short ones
+    G = X.T @ X
+    total = 0.0
+    check = list(range(16)) + [50, 200, ni - 1]
+    for r in range(NI):
+        sl = slice(irp[r], irp[r + 1])
+        Xs, w = X[ici[sl]], iv[sl]
+        if r in check:
+            B = G + (Xs * (alpha * w)[:, None]).T @ Xs
+            b = ((1 + alpha * w)[:, None] * Xs).sum(0)
+            want = np.linalg.solve(B + lam * np.eye(k), b)
+            assert np.abs(Y[r] - want).max() <= 1e-9 * np.abs(want).max(), r
+    assert np.isfinite(li)
+    # whole half-step against the oracle (items only: 400 rows, 6.6M signals)
+    Yo = np.zeros((NI, k))
+    li_o = oracle_lib.qmfo_wals_half_step(Yo, NI, X, NU, k, irp, ici, iv, alpha, lam, NU, NI, 16)
+    assert rel_err_rows(Y, Yo) < FACTOR_TOL
+    assert abs(li - li_o) <= LOSS_TOL * abs(li_o)
+
+
 @pytest.mark.parametrize("nu,ni,nnz,k,dup", [(700, 500, 20000, 128, 0), (900, 300, 9000, 128, 11), (400, 300, 12000, 100, 0),
                                               (500, 400, 8000, 64, 0), (300, 200, 6000, 30, 5), (260, 210, 5000, 96, 0),
                                               (4000, 300, 60000, 128, 0)])
