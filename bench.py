@@ -397,14 +397,24 @@ def run_ours(args, cfg, workload):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic, traffic_src = None, None
+    if world == 1:
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = workload.split()[0].lower()
+            ent = [tj[key + "_user"]["launches"][0], tj[key + "_item"]["launches"][0]]
+            traffic = [float(e["dram_bytes"]) for e in ent]
+            traffic_src = "profiles/" + tj[key + "_user"]["source"] + ", profiles/" + tj[key + "_item"]["source"]
+        except Exception:
+            traffic = None
+    traffic_total = sum(traffic) if traffic and all(t == t for t in traffic) else None
     roofline = {
-        "kernel": "wals_solve_kernel<16> (2 launches/epoch: user rows, item rows)",
+        "kernel": "wals_solve_kernel<%d> (2 launches/epoch: user rows, item rows)" % (sw.kp // 8),
         "bound": "tensor", "achieved": achieved_tf, "peak": fp64_peak_tflops(), "unit": "TFLOP/s",
         "frac": achieved_tf / fp64_peak_tflops(),
-        # dram__bytes_read.sum + dram__bytes_write.sum of the user-rows launch (profiles/r01_solve_final_ncu.csv:
-        # 1.40 GB + 0.50 GB vs 1.71 GB algorithmic: the gathered item factors stay in L2); ncu reports no DRAM
-        # counters for the item-rows launch of the same capture
-        "traffic": 1.90e9 if (workload.startswith("C4") and world == 1) else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one epoch (user rows + item rows), from
+        # the ncu --set full captures summarised in profiles/traffic.json (tools/capture_profiles.sh, tools/ncu_summary.py)
+        "traffic": traffic_total, "traffic_per_launch": traffic, "traffic_source": traffic_src,
         "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json "
                        "has no FP64 entry (its bf16 figure does not apply to an FP64 kernel)",
         "algorithmic_flops_per_epoch": fl, "solve_ms_user_item": [float(np.mean([x[0] for x in solve_ms])),

@@ -53,6 +53,7 @@ constexpr int kEvI = 64;        // items per tile
 constexpr int kEvKC = 32;       // factors per staged chunk
 constexpr int kEvLDB = kEvKC + 4;  // stage row stride in doubles: == 4 mod 16 -> conflict-free fragment loads
 constexpr int kEvSpCap = 2048;  // sorted positives' scores of one unit held in shared memory (else: global)
+constexpr int kEvLinear = 32;   // up to this many positives are counted linearly in the epilogue (else: binary search)
 constexpr int kEvPosSmem = 4096;  // eval_pos_kernel: positives of one user sorted in shared memory
 
 struct EvalParams {
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
     };
     for (int i = 0; i < NS - 1; ++i) issue(i);
 
+    int c0[4] = {0, 0, 0, 0};  // bucket-0 hits of this lane's four user rows over the whole unit
     for (int tile = 0; tile < ntiles; ++tile) {
       const int x0 = xb + tile * kEvI;
       double acc[4][2][2];
@@ -338,14 +340,11 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
         }
       }
       // ---- epilogue: bucket the 16 scores of this lane --------------------------------------------------
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        const int ul = 32 * uh + 8 * mt + (lane >> 2);
-        const int nP = nPs[ul];
-        if (nP < 0) continue;
+      // `sp` / `cn` are passed from two call sites so that the common case (the unit's positives and counters in
+      // shared memory) compiles to LDS / ATOMS instead of generic loads: the profile of the first version had 55 %
+      // of the warp samples in this block, most of them on the dependent generic loads of a binary search.
+      auto bucket_row = [&](int mt, int ul, int nP, const double* sp, int* cn) {
         const double un = unorm[ul];
-        const double* sp = in_smem ? sps + soff[ul] : prm.pos_scores + lp0s[ul];
-        int* cn = in_smem ? cnts + soff[ul] : prm.cnt + lp0s[ul] + (t0 + ul);
         double lo[4], hi[4];
         int a[4], b[4];
         bool live[4];
@@ -360,7 +359,8 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
           b[q] = nP;
           live[q] = (x0 + 16 * iq + 8 * nt + 2 * (lane & 3) + e) < xe;
         }
-        if (nP <= 8) {  // a handful of positives: count them (no dependent search steps)
+        if (nP <= kEvLinear) {  // few positives: count them - independent loads and compares, no dependent search steps
+#pragma unroll 4
           for (int m = 0; m < nP; ++m) {
             const double v = sp[m];
 #pragma unroll
@@ -384,9 +384,22 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
             // a positive's score within the error bound: re-score this pair in the reference's exact order
             const int xl = 16 * iq + 8 * (q >> 1) + 2 * (lane & 3) + (q & 1);
             list[atomicAdd(&misc[0], 1)] = uint16_t((ul << 8) | xl);
+          } else if (a[q] == 0) {
+            ++c0[mt];  // below every positive - by far the most common bucket of a trained model: counted in a register
           } else {
             atomicAdd(cn + a[q], 1);
           }
+        }
+      };
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const int ul = 32 * uh + 8 * mt + (lane >> 2);
+        const int nP = nPs[ul];
+        if (nP < 0) continue;
+        if (in_smem) {
+          bucket_row(mt, ul, nP, sps + soff[ul], cnts + soff[ul]);
+        } else {
+          bucket_row(mt, ul, nP, prm.pos_scores + lp0s[ul], prm.cnt + lp0s[ul] + (t0 + ul));
         }
       }
       __syncthreads();
@@ -403,6 +416,11 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
         __syncthreads();
         if (tid == 0) misc[0] = 0;
       }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {  // the register-held bucket-0 counts join the unit's counters
+      const int ul = 32 * uh + 8 * mt + (lane >> 2);
+      if (nPs[ul] >= 0 && c0[mt] != 0) atomicAdd(in_smem ? cnts + soff[ul] : prm.cnt + lp0s[ul] + (t0 + ul), c0[mt]);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();

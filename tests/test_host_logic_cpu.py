@@ -145,3 +145,75 @@ def test_sharded_wals_two_ranks_gloo(tmp_path, oracle_lib):
     # the 2-rank Gram is the sum of two partial Grams (different association): ~1e-16 relative
     assert rel_err_rows(got["X"], X) < 1e-11 and rel_err_rows(got["Y"], Y) < 1e-11
     assert np.allclose(got["losses"], losses, rtol=1e-12, atol=0)
+
+
+# ---- C5 path: every rank generates only its shard (qmf_b200.datagen.powerlaw_shard_torch) ---------------------
+_PL = dict(nusers=3000, nitems=400, draws=40_000, seed=11, chunk=9_000, k=8)
+
+
+def test_powerlaw_shards_concatenate_to_the_full_problem():
+    """the per-rank shards of the streamed power-law generator are exactly the row ranges of the 1-rank problem,
+    both orientations are transposes of each other, and the popularity law is heavy-tailed"""
+    from qmf_b200.datagen import powerlaw_shard_torch
+    a = _PL
+    full = powerlaw_shard_torch(a["nusers"], a["nitems"], a["draws"], a["seed"], "cpu", 0, 1, chunk_draws=a["chunk"])
+    parts = [powerlaw_shard_torch(a["nusers"], a["nitems"], a["draws"], a["seed"], "cpu", r, 3, chunk_draws=a["chunk"])
+             for r in range(3)]
+    for key in ("csr_user", "csr_item"):
+        for j in (1, 2):
+            assert torch.equal(torch.cat([p[key][j] for p in parts]), full[key][j])
+    assert all(p["ranges"] == parts[0]["ranges"] and p["nnz"] == full["nnz"] for p in parts)
+    assert torch.equal(parts[2]["test_items"], full["test_items"])
+    urp, ucol, uval = full["csr_user"]
+    irp, icol, ival = full["csr_item"]
+    u = torch.repeat_interleave(torch.arange(a["nusers"]), urp[1:] - urp[:-1])
+    i = torch.repeat_interleave(torch.arange(a["nitems"]), irp[1:] - irp[:-1])
+    ka, kb = u * a["nitems"] + ucol.long(), icol.long() * a["nitems"] + i
+    oa, ob = torch.argsort(ka), torch.argsort(kb)
+    assert torch.equal(ka[oa], kb[ob]) and torch.equal(uval[oa], ival[ob])
+    assert len(torch.unique(ka)) == len(ka)                    # distinct cells
+    ilen = (irp[1:] - irp[:-1]).sort(descending=True).values
+    assert ilen[0] > 20 * ilen[len(ilen) // 2]                 # blockbusters vs the median item
+    assert set(uval.unique().tolist()) <= {1.0, 2.0, 3.0, 4.0, 5.0}
+
+
+def _rank_main_presharded(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from qmf_b200.datagen import powerlaw_shard_torch
+    from qmf_b200.wals_dist import ShardedWals
+    a = _PL
+    p = powerlaw_shard_torch(a["nusers"], a["nitems"], a["draws"], a["seed"], "cpu", rank, world, chunk_draws=a["chunk"])
+    sw = ShardedWals(a["nusers"], a["nitems"], a["k"], p["csr_user"], p["csr_item"], torch.device("cpu"), rank, world,
+                     kernels=OracleKernels(), ranges=p["ranges"])
+    sw.set_factors(1, init_factors(a["nitems"], a["k"], 2))
+    losses = [float(sw.epoch(40.0, 0.05)) for _ in range(2)]
+    sw.check_error()
+    if rank == 0:
+        np.savez(out_path, X=sw.get_factors(0).numpy(), Y=sw.get_factors(1).numpy(), losses=np.array(losses))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_presharded_wals_two_ranks_gloo(tmp_path, oracle_lib):
+    """ShardedWals(ranges=...) on shards each rank generated for itself == the oracle on the full problem"""
+    from qmf_b200.datagen import powerlaw_shard_torch
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_rank_main_presharded, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    a = _PL
+    full = powerlaw_shard_torch(a["nusers"], a["nitems"], a["draws"], a["seed"], "cpu", 0, 1, chunk_draws=a["chunk"])
+    ucsr = tuple(np.ascontiguousarray(x.numpy()) for x in full["csr_user"])
+    icsr = tuple(np.ascontiguousarray(x.numpy()) for x in full["csr_item"])
+    NU, NI, k = a["nusers"], a["nitems"], a["k"]
+    X, Y = np.zeros((NU, k)), init_factors(NI, k, 2).copy()
+    losses = []
+    for _ in range(2):
+        oracle_lib.qmfo_wals_half_step(X, NU, Y, NI, k, *ucsr, 40.0, 0.05, NU, NI, 1)
+        losses.append(oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, *icsr, 40.0, 0.05, NU, NI, 1))
+    assert rel_err_rows(got["X"], X) < 1e-11 and rel_err_rows(got["Y"], Y) < 1e-11
+    assert np.allclose(got["losses"], losses, rtol=1e-12, atol=0)

@@ -275,23 +275,32 @@ def test_extremely_long_row_is_built_by_many_ctas(oracle_lib):
     assert abs(lu - lu_o) <= LOSS_TOL * abs(lu_o) and abs(li - li_o) <= LOSS_TOL * abs(li_o)
 
 
+_POWER_LAW = {}
+
+
+def _power_law_problem():
+    """Zipf-like item popularity: one item above kLongMaxParts * kLongSegMin entries (its segments are longer
+    than the minimum), a dozen more above kLongRow with very different lengths, a long tail"""
+    if "p" not in _POWER_LAW:
+        from qmf_b200 import csr_from_coo
+        rng = np.random.default_rng(2024)
+        nu, ni = 1_200_000, 300
+        lens = np.maximum((400_000 / np.arange(1, ni + 1)).astype(np.int64), 40)
+        lens[0] = 1_100_000
+        assert (lens >= 32768).sum() >= 12 and lens[0] > 256 * 4096
+        u = np.concatenate([rng.choice(nu, size=int(n), replace=False) for n in lens]).astype(np.int64)
+        i = np.repeat(np.arange(ni), lens).astype(np.int64)
+        v = rng.integers(1, 6, size=len(u)).astype(np.float64)
+        _POWER_LAW["p"] = (csr_from_coo(u, i, v), csr_from_coo(i, u, v))
+    return _POWER_LAW["p"]
+
+
 @pytest.mark.parametrize("k,mode", [(128, 1), (128, 2), (30, 0)])
 def test_power_law_items_many_long_rows(oracle_lib, k, mode):
-    """Zipf-like item popularity: a dozen items above kLongRow with very different lengths (one of them
-    above kLongMaxParts * kLongSegMin entries, so its segments are longer than the minimum) go through the
-    (row, segment) work list; sampled rows are checked against the oracle's row update and the loss
-    against the per-row terms.  Both solve kernels."""
-    from qmf_b200 import WalsEngineHandle, capi, csr_from_coo
-    rng = np.random.default_rng(2024)
-    nu, ni = 1_300_000, 400
-    lens = np.maximum((1_200_000 / np.arange(1, ni + 1) ** 1.0).astype(np.int64), 40)
-    assert (lens >= 32768).sum() >= 12 and lens[0] > 256 * 4096
-    us = [rng.choice(nu, size=int(n), replace=False) for n in lens]
-    u = np.concatenate(us).astype(np.int64)
-    i = np.repeat(np.arange(ni), lens).astype(np.int64)
-    v = rng.integers(1, 6, size=len(u)).astype(np.float64)
-    uids, urp, uci, uv = csr_from_coo(u, i, v)
-    iids, irp, ici, iv = csr_from_coo(i, u, v)
+    """the (row, segment) work list of the long-row pre-pass, both solve kernels: the item half-step from the
+    GPU's own user factors against the oracle's (factors per row, loss), long rows also against numpy"""
+    from qmf_b200 import WalsEngineHandle, capi
+    (uids, urp, uci, uv), (iids, irp, ici, iv) = _power_law_problem()
     NU, NI = len(uids), len(iids)
     alpha, lam = 40.0, 0.05
     try:
@@ -299,8 +308,7 @@ def test_power_law_items_many_long_rows(oracle_lib, k, mode):
         h = WalsEngineHandle(NU, NI, k)
         h.set_csr(0, urp, uci, uv)
         h.set_csr(1, irp, ici, iv)
-        Y0 = init_factors(NI, k, seed=5)
-        h.set_factors(1, Y0)
+        h.set_factors(1, init_factors(NI, k, seed=5))
         h.half_step(0, alpha, lam)
         X = h.get_factors(0)
         li = h.half_step(1, alpha, lam)
@@ -308,25 +316,27 @@ def test_power_law_items_many_long_rows(oracle_lib, k, mode):
         h.close()
     finally:
         capi.check(capi.lib.qmfb_wals_set_solve_kernel(0))
-    # item rows from the GPU's own user factors: normal equations in numpy (float64, same formulas as
-    # WALSEngine.cpp:277-304), every long row + a few short ones
     G = X.T @ X
-    total = 0.0
-    check = list(range(16)) + [50, 200, ni - 1]
-    for r in range(NI):
+    for r in list(range(14)) + [50, NI - 1]:
         sl = slice(irp[r], irp[r + 1])
         Xs, w = X[ici[sl]], iv[sl]
-        if r in check:
-            B = G + (Xs * (alpha * w)[:, None]).T @ Xs
-            b = ((1 + alpha * w)[:, None] * Xs).sum(0)
-            want = np.linalg.solve(B + lam * np.eye(k), b)
-            assert np.abs(Y[r] - want).max() <= 1e-9 * np.abs(want).max(), r
-    assert np.isfinite(li)
-    # whole half-step against the oracle (items only: 400 rows, 6.6M signals)
-    Yo = np.zeros((NI, k))
-    li_o = oracle_lib.qmfo_wals_half_step(Yo, NI, X, NU, k, irp, ici, iv, alpha, lam, NU, NI, 16)
+        B = G + (Xs * (alpha * w)[:, None]).T @ Xs
+        b = ((1 + alpha * w)[:, None] * Xs).sum(0)
+        want = np.linalg.solve(B + lam * np.eye(k), b)
+        assert np.abs(Y[r] - want).max() <= 1e-9 * np.abs(want).max(), r
+    key = ("oracle", k)
+    if key not in _POWER_LAW:   # X is the same for both kernels (identical per-row arithmetic): one oracle run per k
+        Yo = np.zeros((NI, k))
+        _POWER_LAW[key] = (X.copy(), Yo, oracle_lib.qmfo_wals_half_step(Yo, NI, X, NU, k, irp, ici, iv, alpha, lam, NU, NI, 16))
+    Xo, Yo, li_o = _POWER_LAW[key]
+    assert np.array_equal(X, Xo)
     assert rel_err_rows(Y, Yo) < FACTOR_TOL
-    assert abs(li - li_o) <= LOSS_TOL * abs(li_o)
+    # The loss of a row is c + x^T B x - 2 x^T b with c = sum_s (1 + alpha r_s) (WALSEngine.cpp:286,295-304): for a row of
+    # 1.1e6 signals c ~ 1.3e8 and the three terms cancel to ~1e4, so the reference's own left-to-right sums carry an
+    # absolute error of ~1e-16 * sqrt(n) * c that no other summation order reproduces.  The 1e-12 gate is therefore
+    # applied relative to the magnitude the loss is summed FROM (sum of c over all rows), not to the cancelled result.
+    c_total = float((1.0 + alpha * iv).sum()) / NU / NI
+    assert abs(li - li_o) <= LOSS_TOL * max(abs(li_o), c_total), (li, li_o, c_total)
 
 
 @pytest.mark.parametrize("nu,ni,nnz,k,dup", [(700, 500, 20000, 128, 0), (900, 300, 9000, 128, 11), (400, 300, 12000, 100, 0),

@@ -46,7 +46,7 @@ def main():
         for m in METRICS:
             if m in idx:
                 f.write("%s,%s,%s\n" % (m, units[idx[m]], ",".join(r[idx[m]].replace(",", "") for r in data)))
-    if len(sys.argv) > 5:
+    if len(sys.argv) > 5 and sys.argv[5]:
         path, key = sys.argv[4], sys.argv[5]
         try:
             js = json.load(open(path))
