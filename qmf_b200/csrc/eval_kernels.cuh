@@ -78,14 +78,14 @@ struct EvalParams {
   int sort_in_kernel;          // 0: eval_pos_kernel leaves the scores unsorted (a segmented sort follows)
 };
 
-__host__ __device__ inline size_t eval_smem_bytes(int kp, int stages) {
+__host__ __device__ inline size_t eval_smem_bytes(int kp, int stages, int ng) {
   size_t b = size_t(kEvU) * (kp + 4) * 8;              // U tile
-  b += size_t(stages) * kEvI * kEvLDB * 8;             // item chunk ring
+  b += size_t(ng) * stages * kEvI * kEvLDB * 8;        // item chunk ring of every warp group
   b += size_t(kEvSpCap) * 8;                           // sorted positives
   b += size_t(kEvSpCap + kEvU) * 4;                    // bucket counters
   b += size_t(kEvU) * (8 + 8 + 4 + 4);                 // unorm, sp offset(int64), nP, user idx
-  b += size_t(kEvU) * kEvI * 2;                        // re-score list (uint16)
-  b += 64;                                             // list count, unit id, flags, slot total
+  b += size_t(ng) * kEvU * kEvI * 2;                   // re-score list of every warp group (uint16)
+  b += 64;                                             // unit id, flags, slot total, list counts
   return b;
 }
 
@@ -183,22 +183,31 @@ __global__ void eval_pos_bucket_kernel(const EvalParams prm, int64_t nlabels) {
 }
 
 // ---- 2. all items by DMMA + buckets -----------------------------------------------------------------
-__global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams prm) {
+// NG warp groups of 8 warps share one CTA (one per SM) and one 64-user tile, and take the item tiles of the unit in
+// turn (group g: tiles g, g + NG, ...) with their own cp.async ring, re-score list and NAMED barrier: nothing makes
+// them run in lockstep, so one group's epilogue (search + shared atomics, no DMMA) overlaps the other's DMMA main
+// loop - with a single group the tensor pipe idled through every epilogue (34.8 % DMMA-active in
+// profiles/r02_eval_large_ncu.csv).  NG = 2 whenever the shared memory allows it (k <= 128).
+template <int NG>
+__global__ void __launch_bounds__(kEvThreads * NG) eval_score_kernel(const EvalParams prm) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NTH = kEvThreads * NG;
   const int KP = prm.kp, LDU = KP + 4, NS = prm.stages;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int g = warp >> 3, gw = warp & 7, gtid = tid & (kEvThreads - 1);
   double* utile = reinterpret_cast<double*>(smem);
-  double* ring = utile + size_t(kEvU) * LDU;
-  double* sps = ring + size_t(NS) * kEvI * kEvLDB;
+  double* ring = utile + size_t(kEvU) * LDU + size_t(g) * NS * kEvI * kEvLDB;
+  double* sps = utile + size_t(kEvU) * LDU + size_t(NG) * NS * kEvI * kEvLDB;
   int* cnts = reinterpret_cast<int*>(sps + kEvSpCap);
   double* unorm = reinterpret_cast<double*>(cnts + kEvSpCap + kEvU);
   int64_t* lp0s = reinterpret_cast<int64_t*>(unorm + kEvU);
   int* nPs = reinterpret_cast<int*>(lp0s + kEvU);
   int* soff = nPs + kEvU;                      // offset of the user's positives / counters in sps / cnts
-  uint16_t* list = reinterpret_cast<uint16_t*>(soff + kEvU);
-  int* misc = reinterpret_cast<int*>(list + kEvU * kEvI);  // [0] list count, [1] unit, [2] positives-in-smem flag
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int uh = warp & 1, iq = warp >> 1;     // users 32 uh .. +31 (4 row tiles), items 16 iq .. +15 (2 column tiles)
+  uint16_t* list = reinterpret_cast<uint16_t*>(soff + kEvU) + size_t(g) * kEvU * kEvI;
+  int* misc = reinterpret_cast<int*>(reinterpret_cast<uint16_t*>(soff + kEvU) + size_t(NG) * kEvU * kEvI);  // [1] unit, [2] positives-in-smem flag, [3] slots
+  int* lcount = misc + 8 + g;                  // this group's re-score list length
+  auto group_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kEvThreads) : "memory"); };
+  const int uh = gw & 1, iq = gw >> 1;         // users 32 uh .. +31 (4 row tiles), items 16 iq .. +15 (2 column tiles)
   const int ngroups = (prm.nT + kEvU - 1) / kEvU;
   const int nunits = ngroups * prm.nsplit;
   const int nchunks = KP / kEvKC;
@@ -234,12 +243,13 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
       if (lane == 31) {
         misc[2] = (incl <= kEvSpCap) ? 1 : 0;
         misc[3] = incl;
-        misc[0] = 0;
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg) misc[8 + gg] = 0;
       }
     }
     {  // U tile: 16-byte cp.async, rows of users past the end are rows of the last valid user (never bucketed)
       const int ppr = KP / 2;
-      for (int q = tid; q < kEvU * ppr; q += kEvThreads) {
+      for (int q = tid; q < kEvU * ppr; q += NTH) {
         const int r = q / ppr, piece = q % ppr;
         const int t = t0 + min(r, nU - 1);
         ev_cp_async16(utile + size_t(r) * LDU + piece * 2, prm.U + int64_t(prm.test_users[t]) * prm.ldu + piece * 2);
@@ -259,17 +269,19 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
       return lo;
     };
     {  // ||u||_2 (4 threads per user), counters, sorted positives
-      const int r = tid >> 2, q = tid & 3;
-      double s = 0.0;
-      for (int f = q; f < prm.k; f += 4) {
-        const double v = utile[size_t(r) * LDU + f];
-        s = fma(v, v, s);
+      if (tid < 4 * kEvU) {  // whole warps
+        const int r = tid >> 2, q = tid & 3;
+        double s = 0.0;
+        for (int f = q; f < prm.k; f += 4) {
+          const double v = utile[size_t(r) * LDU + f];
+          s = fma(v, v, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (q == 0) unorm[r] = sqrt(s);
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (q == 0) unorm[r] = sqrt(s);
       if (in_smem) {  // flattened over (user, slot): no serial loop over the 64 users
-        for (int qq = tid; qq < ntot; qq += kEvThreads) {
+        for (int qq = tid; qq < ntot; qq += NTH) {
           cnts[qq] = 0;
           const int u = owner(qq), i = qq - soff[u];
           if (i < nPs[u]) sps[qq] = prm.pos_scores[lp0s[u] + i];
@@ -280,14 +292,15 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
 
     // ---- item tiles ------------------------------------------------------------------------------------
     const int ntiles = (xe - xb + kEvI - 1) / kEvI;
-    const int total = ntiles * nchunks;
-    auto issue = [&](int idx) {  // chunk idx = tile * nchunks + c
+    const int ntiles_g = ntiles > g ? (ntiles - g + NG - 1) / NG : 0;  // this group's tiles: g, g + NG, ...
+    const int total = ntiles_g * nchunks;
+    auto issue = [&](int idx) {  // chunk idx = (local tile) * nchunks + c
       if (idx < total) {
-        const int tile = idx / nchunks, c = idx % nchunks;
+        const int tile = g + NG * (idx / nchunks), c = idx % nchunks;
         double* st = ring + size_t(idx % NS) * kEvI * kEvLDB;
 #pragma unroll
         for (int m = 0; m < (kEvI * kEvKC / 2) / kEvThreads; ++m) {
-          const int q = tid + kEvThreads * m, r = q / (kEvKC / 2), piece = q % (kEvKC / 2);
+          const int q = gtid + kEvThreads * m, r = q / (kEvKC / 2), piece = q % (kEvKC / 2);
           const int x = min(xb + tile * kEvI + r, prm.nitems - 1);
           ev_cp_async16(st + r * kEvLDB + piece * 2, prm.V + int64_t(x) * prm.ldv + c * kEvKC + piece * 2);
         }
@@ -297,7 +310,8 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
     for (int i = 0; i < NS - 1; ++i) issue(i);
 
     int c0[4] = {0, 0, 0, 0};  // bucket-0 hits of this lane's four user rows over the whole unit
-    for (int tile = 0; tile < ntiles; ++tile) {
+    for (int lt = 0; lt < ntiles_g; ++lt) {
+      const int tile = g + NG * lt;
       const int x0 = xb + tile * kEvI;
       double acc[4][2][2];
 #pragma unroll
@@ -316,13 +330,13 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
           vb[nt][e] = (ok && prm.bias != nullptr) ? __ldg(prm.bias + x) : 0.0;
         }
       for (int c = 0; c < nchunks; ++c) {
-        const int idx = tile * nchunks + c;
+        const int idx = lt * nchunks + c;
         if (NS == 4) {
           asm volatile("cp.async.wait_group 2;" ::: "memory");
         } else {
           asm volatile("cp.async.wait_group 1;" ::: "memory");
         }
-        __syncthreads();  // chunk idx landed for everyone; the stage consumed in the previous iteration is free
+        group_bar();  // chunk idx landed for the whole group; the stage consumed in the previous iteration is free
         issue(idx + NS - 1);
         const double* st = ring + size_t(idx % NS) * kEvI * kEvLDB + size_t(16 * iq + (lane >> 2)) * kEvLDB + (lane & 3);
         const double* ua = utile + size_t(32 * uh + (lane >> 2)) * LDU + c * kEvKC + (lane & 3);
@@ -383,7 +397,7 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
           if (a[q] < nP && sp[a[q]] <= hi[q]) {
             // a positive's score within the error bound: re-score this pair in the reference's exact order
             const int xl = 16 * iq + 8 * (q >> 1) + 2 * (lane & 3) + (q & 1);
-            list[atomicAdd(&misc[0], 1)] = uint16_t((ul << 8) | xl);
+            list[atomicAdd(lcount, 1)] = uint16_t((ul << 8) | xl);
           } else if (a[q] == 0) {
             ++c0[mt];  // below every positive - by far the most common bucket of a trained model: counted in a register
           } else {
@@ -402,10 +416,10 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
           bucket_row(mt, ul, nP, prm.pos_scores + lp0s[ul], prm.cnt + lp0s[ul] + (t0 + ul));
         }
       }
-      __syncthreads();
-      const int nlist = misc[0];
+      group_bar();
+      const int nlist = *lcount;
       if (nlist > 0) {
-        for (int e = tid; e < nlist; e += kEvThreads) {
+        for (int e = gtid; e < nlist; e += kEvThreads) {
           const int ul = list[e] >> 8, x = x0 + (list[e] & 255);
           const double s = eval_exact_score(utile + size_t(ul) * LDU, prm.V + int64_t(x) * prm.ldv,
                                             prm.bias != nullptr ? prm.bias[x] : 0.0, prm.k);
@@ -413,8 +427,8 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
           int* cn = in_smem ? cnts + soff[ul] : prm.cnt + lp0s[ul] + (t0 + ul);
           atomicAdd(cn + eval_lower_bound(sp, nPs[ul], s), 1);
         }
-        __syncthreads();
-        if (tid == 0) misc[0] = 0;
+        group_bar();
+        if (gtid == 0) *lcount = 0;
       }
     }
 #pragma unroll
@@ -427,7 +441,7 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
     // ---- the positive ITEMS of this item range were bucketed like negatives: take them out again, at the
     //      bucket eval_pos_bucket_kernel computed from their exact score; then the unit's counters go to
     //      global memory (the item ranges of one user add up).  Flattened over (user, slot).
-    for (int qq = tid; qq < ntot; qq += kEvThreads) {
+    for (int qq = tid; qq < ntot; qq += NTH) {
       const int u = owner(qq), i = qq - soff[u];
       if (i < nPs[u]) {
         const int item = prm.label_items[lp0s[u] + i];
@@ -439,7 +453,7 @@ __global__ void __launch_bounds__(kEvThreads) eval_score_kernel(const EvalParams
     }
     if (in_smem) {
       __syncthreads();
-      for (int qq = tid; qq < ntot; qq += kEvThreads) {
+      for (int qq = tid; qq < ntot; qq += NTH) {
         const int u = owner(qq), i = qq - soff[u];
         if (u < nU && i <= nPs[u]) {
           const int v = cnts[qq];

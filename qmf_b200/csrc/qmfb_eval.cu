@@ -141,14 +141,18 @@ int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double*
   auto st = static_cast<cudaStream_t>(stream);
   QMFB_CUDA(cudaMemsetAsync(cnt, 0, size_t(nlabels + nT) * sizeof(int32_t), st));
   if (nT == 0) return QMFB_OK;
-  const int stages = kp <= 128 ? 4 : 3;
-  const size_t smem = eval_smem_bytes(kp, stages);
+  // k <= 128: two warp groups per CTA (512 threads) with a 3-stage ring each; above, the 64-user tile alone takes
+  // 133 KB and one group with a 3-stage ring is what fits
+  const int ng = kp <= 128 ? 2 : 1;
+  const int stages = 3;
+  const size_t smem = eval_smem_bytes(kp, stages, ng);
+  auto kernel = ng == 2 ? eval_score_kernel<2> : eval_score_kernel<1>;
   // per device / context attribute: set on every call (cheap), a process may use several devices
-  QMFB_CUDA(cudaFuncSetAttribute(eval_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  QMFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int dev = 0, sms = 148, occ = 1;
   QMFB_CUDA(cudaGetDevice(&dev));
   QMFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  QMFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eval_score_kernel, kEvThreads, smem));
+  QMFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kEvThreads * ng, smem));
   if (occ < 1) return set_error(QMFB_ERR_UNSUPPORTED, "eval_score_kernel does not fit on an SM (nfactors %d)", k);
   double* vnorm = nullptr;  // | nitems norms | unit counter | nlabels positive buckets |
   QMFB_CUDA(cudaMallocAsync(&vnorm, size_t(nitems) * 8 + 16 + size_t(std::max<int64_t>(nlabels, 1)) * 4, st));
@@ -187,7 +191,7 @@ int qmfb_eval_rank_dev(void* stream, const double* U, int64_t ldu, const double*
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) {
-    eval_score_kernel<<<grid, kEvThreads, smem, st>>>(p);
+    kernel<<<grid, kEvThreads * ng, smem, st>>>(p);
     e = cudaGetLastError();
   }
   cudaFreeAsync(vnorm, st);
