@@ -472,6 +472,32 @@ def run_ours(args, cfg, workload):
             e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "nnz/s", "h2d_bytes_per_step": world * ni * k * 8,
                    "d2h_bytes_per_step": (nu + ni) * k * 8 + 8 * world, "ms_per_step": e2e_ms,
                    "api": "ShardedWals.epoch_host: pinned host factors in/out on every rank (CUDA events, max over ranks)"}
+            # The same epoch through the engine-level C ABI that `wals --ngpus N` / qmf::WALSEngine bind: ONE process
+            # (rank 0) drives all N GPUs with qmfb_wals_sharded_epoch_host while the other ranks sleep on a CPU barrier.
+            cpu_group = dist.new_group(backend="gloo")
+            if rank == 0:
+                try:
+                    from qmf_b200.wals import ShardedWalsHandle
+                    hs = ShardedWalsHandle(nu, ni, k, list(range(world)))
+                    for side, (rp, col, val) in enumerate((csr_user, csr_item)):
+                        hs.set_csr(side, rp.cpu().numpy(), col.cpu().numpy(), val.cpu().numpy())
+                    uo = torch.empty((nu, k), dtype=torch.float64).pin_memory()
+                    io = torch.empty((ni, k), dtype=torch.float64).pin_memory()
+                    for _ in range(2):
+                        l2 = hs.epoch_host(ALPHA, LAMBDA, item_in.numpy(), uo.numpy(), io.numpy())
+                    tt = time.perf_counter()
+                    for _ in range(args.steps):
+                        l2 = hs.epoch_host(ALPHA, LAMBDA, item_in.numpy(), uo.numpy(), io.numpy())
+                    cabi_ms = (time.perf_counter() - tt) * 1e3 / args.steps
+                    e2e["c_abi"] = {"value": nnz / (cabi_ms * 1e-3), "unit": "nnz/s", "ms_per_step": cabi_ms, "loss": l2,
+                                    "h2d_bytes_per_step": world * ni * k * 8, "d2h_bytes_per_step": (nu + ni) * k * 8 + 8,
+                                    "launches": hs.launch_count(),
+                                    "api": "qmfb_wals_sharded_epoch_host: one process, %d GPUs, pinned host buffers, wall clock "
+                                           "around the synchronous call (what `wals --ngpus %d` binds)" % (world, world)}
+                    hs.close()
+                except Exception as ex:  # noqa: BLE001 - reported in the line, the device-timed numbers stand
+                    e2e["c_abi"] = {"error": str(ex)[:300]}
+            dist.barrier(group=cpu_group)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -620,7 +646,8 @@ def run_c5(args):
     sums = []
     for name in ("auc", "p@10"):
         out = np.empty(nT, dtype=np.float64)
-        capi.check(capi.lib.qmfb_rank_metrics(name.encode(), cnt_h, lp_h, nT, ni, 0, out))
+        # host threads: this rank's share of the box's cores (8 ranks x all cores oversubscribed the host: 41.7 s -> see line)
+        capi.check(capi.lib.qmfb_rank_metrics(name.encode(), cnt_h, lp_h, nT, ni, max(1, (os.cpu_count() or 1) // world), out))
         sums.append(float(out.sum()))
     t_host = time.perf_counter() - t_host
     tot = torch.tensor(sums + [float(cnt_h.sum())], dtype=torch.float64, device=device)

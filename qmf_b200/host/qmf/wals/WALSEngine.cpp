@@ -34,6 +34,18 @@ WALSEngine::~WALSEngine() {
 void WALSEngine::init(const std::vector<DatasetElem>& dataset) {
   CHECK(!userFactors_ && !itemFactors_) << "engine was already initialized with train data";
   CHECK(!dataset.empty()) << "empty training dataset";
+  // The GPU row solve is a Cholesky factorisation: every row's A = Y^T Y + sum alpha r y y^T + lambda I must be positive
+  // definite.  The reference's dsysv (Bunch-Kaufman, qmf/Matrix.cpp:81-96) also solves the indefinite systems that
+  // lambda <= 0 on rank-deficient rows or negative confidences (alpha r < 0) can produce; this engine states the
+  // restriction BEFORE training instead of failing with QMFB_ERR_NOT_SPD in the middle of it.
+  CHECK_GT(config_.regularizationLambda, 0.0)
+    << "qmf_b200 requires --regularization_lambda > 0 (per-row Cholesky solve; the reference's dsysv accepts lambda <= 0)";
+  {
+    bool negative = false;
+    for (const auto& e : dataset) negative |= config_.confidenceWeight * e.value < 0.0;
+    CHECK(!negative) << "qmf_b200 requires confidence_weight * value >= 0 for every training signal (per-row Cholesky solve; "
+                        "the reference's dsysv accepts indefinite rows)";
+  }
   // Dense indices + both CSR orientations are built on the GPU (qmfb_signals_*): idx = rank of the
   // raw id among the distinct ids, rows by row id, cells by column id - what IdIndex +
   // groupSignals / sortDataset produce (qmf/wals/WALSEngine.cpp:130-163), without the two host

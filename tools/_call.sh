@@ -1,5 +1,4 @@
 set -x
 R=gpurun_out
-nvidia-smi -L | head -8
-timeout 540 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --workload c5 --steps 3 --warmup 1 > $R/r02_bench_c5_n8.json 2> $R/r02_bench_c5_n8.err
-cat $R/r02_bench_c5_n8.json; tail -15 $R/r02_bench_c5_n8.err
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29546 bench.py --gpus 8 --steps 5 --warmup 3 > $R/r02_bench_n8.json 2> $R/r02_bench_n8.err
+grep '^{"metric"' $R/r02_bench_n8.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['frac'], d['loss'], json.dumps(d['e2e']))"; tail -5 $R/r02_bench_n8.err
