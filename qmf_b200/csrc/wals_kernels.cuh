@@ -54,7 +54,19 @@ constexpr int kTU = 1;
 #ifndef QMFB_KSTAGES
 #define QMFB_KSTAGES 5
 #endif
-constexpr int kStages = QMFB_KSTAGES;   // ring depth
+constexpr int kStages = QMFB_KSTAGES;   // ring depth (k > 64)
+// k <= 64 (NT <= 8): the rows are short and cheap, what counts is how many are in flight per SM - a shallower ring and a
+// tighter register budget buy more resident CTAs (measured on C3 / C1)
+// (gpurun r02_occ_variants.log, C3 epoch: ring 5 / 4 CTAs 10.85 ms, ring 4 / 5 CTAs 10.57, ring 3 / 5 CTAs 10.48, ring 3 / 6 CTAs 10.26)
+#ifndef QMFB_RING_SMALL
+#define QMFB_RING_SMALL 3
+#endif
+#ifndef QMFB_OCC8
+#define QMFB_OCC8 6    // resident CTAs per SM the NT = 8 kernel is compiled for (80 registers, 32.5 KB)
+#endif
+#ifndef QMFB_OCC4
+#define QMFB_OCC4 12   // ... the NT = 4 kernel (79 registers, 17.3 KB)
+#endif
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers
@@ -126,23 +138,23 @@ struct WalsSmem {
   static constexpr int NTHREADS = NWARPS * 32;  // == 2 * KP
   static constexpr int NTILE_A = NT * (NT + 1) / 2;
   static constexpr int NTILE = NTILE_A + NT;    // + one tile column for b
-  static constexpr int kRing = kStages;         // ring depth of the gather pipeline
-  static constexpr int kAhead = kStages - 2;    // chunks in flight beyond the one being consumed: the stage refilled
+  static constexpr int kRing = NT <= 8 ? QMFB_RING_SMALL : kStages;  // ring depth of the gather pipeline
+  static constexpr int kAhead = kRing - 2;      // chunks in flight beyond the one being consumed: the stage refilled
                                                 // was consumed TWO chunks ago (nobody waits for the slowest warp)
-  static constexpr size_t kStageBytes = size_t(kStages) * kChunk * LD * 8;
+  static constexpr size_t kStageBytes = size_t(kRing) * kChunk * LD * 8;
   static constexpr size_t kTileBytes = size_t(NTILE) * 64 * 8;
   static constexpr size_t kMainBytes = kStageBytes > kTileBytes ? kStageBytes : kTileBytes;
   static constexpr size_t kOffStage = 0;
   static constexpr size_t kOffTiles = 0;                                     // aliases the staging ring
-  static constexpr size_t kOffWts = kMainBytes;                              // kStages*2*kChunk doubles
-  static constexpr size_t kOffW = kOffWts + size_t(kStages) * 2 * kChunk * 8;  // NT inverse diagonal tiles
+  static constexpr size_t kOffWts = kMainBytes;                              // kRing*2*kChunk doubles
+  static constexpr size_t kOffW = kOffWts + size_t(kRing) * 2 * kChunk * 8;  // NT inverse diagonal tiles
   static constexpr size_t kOffB = kOffW + size_t(NT) * 64 * 8;               // b copy (KP)
   static constexpr size_t kOffX = kOffB + size_t(KP) * 8;                    // x (KP)
   static constexpr size_t kOffR = kOffX + size_t(KP) * 8;                    // back-substitution rhs (8)
   static constexpr size_t kOffFs = kOffR + 64;                               // solve barriers F/S/G (8 doubles) + pivot-row scratch (16 doubles)
   static constexpr size_t kOffBh = kOffFs + 256;                             // per-warp partial sum of (1 + alpha r) (NWARPS, padded to 8)
-  static constexpr size_t kOffBar = kOffBh + 64;                             // full[kStages], empty[kStages]
-  static constexpr size_t kOffRow = kOffBar + size_t(kStages) * 16;          // 2 row slots x 32 bytes
+  static constexpr size_t kOffBar = kOffBh + 64;                             // full[kRing], empty[kRing]
+  static constexpr size_t kOffRow = kOffBar + size_t(kRing) * 16;            // 2 row slots x 32 bytes
   static constexpr size_t kBytes = kOffRow + 64;
 
   // tile (I,J), I <= J <= NT (J == NT is the b column), row-major upper storage
@@ -279,6 +291,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) gram_partial_kernel(co
   // partial[part0 + b]: the parts and the order inside a part depend only on the row range, so the
   // reduced Gram is bit-identical however the parts are dealt to devices (qmfb_wals_sharded_*)
   using SM = WalsSmem<NT>;
+  constexpr int kStages = SM::kRing;  // (shadows the global ring depth: this layout's)
   extern __shared__ __align__(128) unsigned char smem[];
   double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
   double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
@@ -453,6 +466,7 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS) long_row_partial_kerne
   const int nseg = prm.plan->nseg;
   if (int(blockIdx.x) >= nseg) return;
   const int nlong = prm.plan->nlong;
+  constexpr int kStages = SM::kRing;  // (shadows the global ring depth: this layout's)
   extern __shared__ __align__(128) unsigned char smem[];
   double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
   double* wts = reinterpret_cast<double*>(smem + SM::kOffWts);
@@ -1376,7 +1390,7 @@ __device__ __forceinline__ bool solve_row(unsigned char* smem, double* gtiles) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >= 8 ? 4 : 8))) wals_solve_kernel(const SolveParams prm) {
+__global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >= 8 ? QMFB_OCC8 : QMFB_OCC4))) wals_solve_kernel(const SolveParams prm) {
   using SM = WalsSmem<NT>;
   extern __shared__ __align__(128) unsigned char smem[];
   double* stagebuf = reinterpret_cast<double*>(smem + SM::kOffStage);
@@ -1389,12 +1403,12 @@ __global__ void __launch_bounds__(WalsSmem<NT>::NTHREADS, (NT >= 12 ? 2 : (NT >=
   double* fscratch = reinterpret_cast<double*>(smem + SM::kOffFs);
   double* bhalf = reinterpret_cast<double*>(smem + SM::kOffBh);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
-  uint64_t* empty = full + kStages;
+  uint64_t* empty = full + SM::kRing;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, tid = threadIdx.x;
   constexpr int TPR = SM::KP / 2;  // threads per gathered row (16 bytes each); 4 rows per pass
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < SM::kRing; ++s) {
       mbar_init(&full[s], 32 + kChunk);  // gathering warp: one deferred cp.async arrival per lane + weight writers
       mbar_init(&empty[s], SM::NWARPS);
     }
