@@ -41,3 +41,18 @@ def test_reference_gtests_compile_and_pass_against_the_host_tree():
         assert out.returncode == 0 and "[  PASSED  ]" in out.stdout, (t, out.stdout[-2000:], out.stderr[-2000:])
         total += int(out.stdout.split("[  PASSED  ]")[1].split()[0])
     assert total == 26
+
+
+def test_wals_binary_states_the_cholesky_restriction_before_training(tmp_path):
+    """`--regularization_lambda 0` and negative confidences give indefinite rows that the reference's dsysv solves and a
+    Cholesky cannot: the engine must say so in WALSEngine::init (no GPU work has happened yet), not abort mid-training."""
+    train = tmp_path / "train.txt"
+    train.write_text("".join("%d %d %d\n" % (u, i, 1 + (u + i) % 3) for u in range(1, 30) for i in range(1, 20, 1 + u % 3)))
+    wals = os.path.join(HOST, "bin", "wals")
+    out = subprocess.run([wals, "--train_dataset=%s" % train, "--nfactors=4", "--nepochs=1", "--regularization_lambda=0"],
+                         capture_output=True, text=True)
+    assert out.returncode != 0 and "regularization_lambda > 0" in out.stderr, out.stderr[-500:]
+    neg = tmp_path / "neg.txt"
+    neg.write_text(train.read_text() + "3 4 -2\n")
+    out = subprocess.run([wals, "--train_dataset=%s" % neg, "--nfactors=4", "--nepochs=1"], capture_output=True, text=True)
+    assert out.returncode != 0 and "confidence_weight * value >= 0" in out.stderr, out.stderr[-500:]
