@@ -415,7 +415,7 @@ def run_ours(args, cfg, workload):
         # dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one epoch (user rows + item rows), from
         # the ncu --set full captures summarised in profiles/traffic.json (tools/capture_profiles.sh, tools/ncu_summary.py)
         "traffic": traffic_total, "traffic_per_launch": traffic, "traffic_source": traffic_src,
-        "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json "
+        "peak_source": "builder-measured FP64 DMMA peak on this pool's B200 (profiles/fp64_peak.json, profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json "
                        "has no FP64 entry (its bf16 figure does not apply to an FP64 kernel)",
         "algorithmic_flops_per_epoch": fl, "solve_ms_user_item": [float(np.mean([x[0] for x in solve_ms])),
                                                                   float(np.mean([x[1] for x in solve_ms]))],

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE — minimal stand-in for <gflags/gflags.h> (absent from this image) so the
 // UNMODIFIED reference mains (qmf/wals.cpp:26-50, qmf/bpr.cpp:28-59) compile. Supports
 // DEFINE_{bool,int32,uint64,double,string}, -f=v / --f=v / --f v / --flag / --noflag.
-// Not part of the product; used only by oracle/build_ref.sh.
+// Not part of the product; used only by oracle/Makefile (the recipe that compiles the unmodified reference into oracle/_ref/).
 #pragma once
 #include <cstdint>
 #include <cstdlib>

@@ -3,7 +3,7 @@
 // reference actually uses are provided (LOG, VLOG, CHECK, CHECK_EQ/NE/GT/GE/LT/LE, DCHECK).
 // Doubles are streamed with 17 significant digits so the reference's own log lines
 // ("epoch N: train loss = ...", qmf/wals/WALSEngine.cpp:92) carry full FP64 precision.
-// Not part of the product; used only by oracle/build_ref.sh.
+// Not part of the product; used only by oracle/Makefile (the recipe that compiles the unmodified reference into oracle/_ref/).
 #pragma once
 #include <cstdlib>
 #include <iomanip>

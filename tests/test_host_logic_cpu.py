@@ -217,3 +217,54 @@ def test_presharded_wals_two_ranks_gloo(tmp_path, oracle_lib):
         losses.append(oracle_lib.qmfo_wals_half_step(Y, NI, X, NU, k, *icsr, 40.0, 0.05, NU, NI, 1))
     assert rel_err_rows(got["X"], X) < 1e-11 and rel_err_rows(got["Y"], Y) < 1e-11
     assert np.allclose(got["losses"], losses, rtol=1e-12, atol=0)
+
+
+class _FailingKernels(OracleKernels):
+    """raises the NOT_SPD flag in the USER half-step on rank 1 only (the launcher clears scratch before every solve)"""
+
+    def __init__(self, rank):
+        super().__init__()
+        self.rank, self.calls = rank, 0
+
+    def solve(self, X, row_offset, Y, k, row_ptr, col, val, order, gram, alpha, lam, row_loss, loss_sum, scratch, nnz=-1):
+        scratch.zero_()
+        super().solve(X, row_offset, Y, k, row_ptr, col, val, order, gram, alpha, lam, row_loss, loss_sum, scratch, nnz)
+        if self.rank == 1 and self.calls == 0:
+            scratch[1] = 1
+        self.calls += 1
+
+
+def _rank_main_not_spd(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from qmf_b200.wals_dist import ShardedWals
+    NU, NI, k, ucsr, icsr, Y0 = _problem()
+    t = lambda a: tuple(torch.from_numpy(np.ascontiguousarray(x)) for x in a)
+    sw = ShardedWals(NU, NI, k, t(ucsr), t(icsr), torch.device("cpu"), rank, world, kernels=_FailingKernels(rank))
+    sw.set_factors(1, Y0)
+    sw.epoch(40.0, 0.05)           # the flag is raised in the user half-step and must survive the item half-step
+    raised = False
+    try:
+        sw.check_error()
+    except RuntimeError:
+        raised = True
+    again = False
+    try:
+        sw.check_error()           # cleared by the first check
+    except RuntimeError:
+        again = True
+    open(os.path.join(out_dir, "r%d.txt" % rank), "w").write("%d %d" % (raised, again))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_not_spd_flag_is_sticky_and_raised_on_every_rank(tmp_path, oracle_lib):
+    """a non-positive pivot in the user half-step on ONE rank must not be lost when the launcher clears the
+    flag for the item half-step, and every rank must raise (the flag travels in the loss allreduce)"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_rank_main_not_spd, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(str(tmp_path / ("r%d.txt" % r))).read() == "1 0"
