@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALPHA, LAMBDA = 40.0, 0.05          # reference defaults (qmf/wals.cpp:28-29)
+L2_NOTE = "inputs (2.9 GB) larger than the 126 MB L2; no flush"
 
 
 def fp64_peak_tflops():
@@ -202,8 +203,10 @@ def run_reference(args, cfg, workload):
         "impl": "reference", "metric": "wals_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(meas)) * 1e3,
         "est_epoch_s": epoch_s, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        # the same config object as our arm prints for this N (the last three keys describe OUR arm's run of the workload)
         "data": "synthetic", "config": {"workload": workload, "nusers": nu, "nitems": ni, "nnz": nnz, "nfactors": k,
-                                        "alpha": ALPHA, "lambda": LAMBDA},
+                                        "alpha": ALPHA, "lambda": LAMBDA, "parallelism": "rows x%d" % args.gpus,
+                                        "exchange": "p2p" if args.gpus > 1 else "none", "l2": L2_NOTE},
         "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": threads if kind == "reference" else 1, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -532,7 +535,7 @@ def run_ours(args, cfg, workload):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "nusers": nu, "nitems": ni, "nnz": nnz, "nfactors": k, "alpha": ALPHA,
                        "lambda": LAMBDA, "parallelism": "rows x%d" % world, "exchange": sw.exchange if world > 1 else "none",
-                       "l2": "inputs (2.9 GB) larger than the 126 MB L2; no flush"},
+                       "l2": L2_NOTE},
             "loss": loss_value, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
             "cpu_baseline": cpu_baseline, "bpr": bpr, "eval": evalr, "lib": os.path.relpath(capi.LIB_PATH, ROOT),
         }
