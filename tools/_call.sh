@@ -1,4 +1,11 @@
 set -x
 R=gpurun_out
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29547 bench.py --gpus 4 --steps 5 --warmup 3 > $R/r02_bench_n4.json 2> $R/r02_bench_n4.err
-grep '^{"metric"' $R/r02_bench_n4.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['frac'], d['loss'], json.dumps(d['e2e'])[:900])"; tail -3 $R/r02_bench_n4.err
+S="python tools/ncu_summary.py"
+NCU="ncu --set full --clock-control none --import-source on"
+T=$R/traffic.json
+cp profiles/traffic.json $T
+timeout 200 python -m pytest tests/test_cli_gpu.py -x -q 2>&1 | tail -3
+timeout 300 $NCU -k regex:bpr_epoch -s 2 -c 1 -f -o $R/r02_bpr_large_v2 python tools/run_section.py bpr_large > $R/ncu_bpr.log 2>&1
+$S $R/r02_bpr_large_v2.ncu-rep $R/r02_bpr_large_v2_ncu.csv "ncu --set full, bpr_epoch_kernel<2> with the warp-wide membership test, 4M x 1M x k=64 shape" $T bpr_large
+ncu -i $R/r02_bpr_large_v2.ncu-rep --page source --csv --print-source cuda,sass > /tmp/src.csv 2>/dev/null && python tools/ncu_lines.py /tmp/src.csv 0 25 > $R/r02_bpr_large_v2_lines.txt 2>&1
+rm -f $R/*.ncu-rep
