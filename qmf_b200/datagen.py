@@ -13,7 +13,8 @@ CONFIGS = {
     "c3": (138_000, 27_000, 20_000_000, 64),
     "c4": (480_000, 17_800, 100_000_000, 128),
     # power-law (powerlaw_shard_torch): user degree by a rank-size law with exponent 1/1.1 clipped to
-    # [1, 1e5], item popularity Zipf(1.0); nnz is the number of draws (the distinct cells are ~3 % fewer)
+    # [1, 1e5], item popularity Zipf(1.0); nnz is the number of DRAWS - heavy users hit the head items repeatedly,
+    # so the distinct cells are fewer (722 M of 1 B at full size)
     "c5": (10_000_000, 1_000_000, 1_000_000_000, 128),
 }
 
@@ -97,8 +98,9 @@ def _powerlaw_chunk_keys(deg_dev, u0, u1, nitems, seed, chunk_index, device, mul
 
 def _cell_values(keys):
     """weight of a cell in {1..5}, a pure function of the cell so both orientations agree without storing it"""
+    import torch
     h = (keys * 2654435761 + 0x9E3779B9) & 0x7FFFFFFF
-    return ((h >> 7) % 5 + 1).to(dtype=__import__("torch").float64)
+    return ((h >> 7) % 5 + 1).to(dtype=torch.float64)
 
 
 def powerlaw_shard_torch(nusers, nitems, nnz, seed, device, rank=0, world=1, chunk_draws=100_000_000):
