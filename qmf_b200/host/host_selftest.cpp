@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <qmf/DatasetReader.h>
 #include <qmf/Engine.h>
+#include <qmf/FactorData.h>
 #include <qmf/Matrix.h>
 #include <qmf/metrics/Metrics.h>
 #include <qmf/utils/Util.h>
@@ -207,6 +208,47 @@ int main() {
         if (want && got) EXPECT(g.userId == u && g.itemId == i && std::memcmp(&g.value, &w, sizeof w) == 0);
       }
     }
+    std::remove(path.c_str());
+  }
+  // FactorData::setFactors(file): the mapped multi-threaded reader == the reference's getline + sscanf("%lf") loop
+  // (qmf/FactorData.h:74-100), bit for bit, on a 3 MB file of mixed number formats; extra lines are ignored, a short file
+  // sets what it has and leaves the rest untouched
+  {
+    const std::string path = "/tmp/qmf_b200_selftest_dist.txt";
+    const size_t n = 1500, k = 96;  // 144 000 values
+    {
+      std::mt19937_64 g(11);
+      std::uniform_real_distribution<double> U(-0.01, 0.01);
+      std::ofstream out(path);
+      char buf[128];
+      for (size_t i = 0; i < n * k + 37; ++i) {   // 37 extra lines
+        const double v = U(g);
+        switch (i % 9) {
+          case 0: std::snprintf(buf, sizeof buf, "%.9f\n", v); break;                 // gen_uniform's format
+          case 1: std::snprintf(buf, sizeof buf, "  %.17g\r\n", v); break;             // leading blanks, CRLF, 17 digits
+          case 2: std::snprintf(buf, sizeof buf, "%.3e trailing text\n", v); break;     // exponent + ignored tail
+          case 3: std::snprintf(buf, sizeof buf, "\t%d\n", int(i % 1000) - 500); break;  // integers
+          case 4: std::snprintf(buf, sizeof buf, "%.12f 7.5\n", v); break;             // only the first field counts
+          case 5: std::snprintf(buf, sizeof buf, "+%.6f\n", std::fabs(v)); break;
+          case 6: std::snprintf(buf, sizeof buf, "0x1.8p-%d\n", int(i % 20)); break;    // hex float
+          case 7: std::snprintf(buf, sizeof buf, ".%05d\n", int(i % 100000)); break;
+          default: std::snprintf(buf, sizeof buf, "%.20f\n", v); break;               // long mantissa
+        }
+        out << buf;
+      }
+    }
+    qmf::FactorData a(n, k), b(n, k);
+    a.setFactorsSequential(path);
+    b.setFactors(path);
+    EXPECT(std::memcmp(a.getFactors().data(), b.getFactors().data(), n * k * sizeof(double)) == 0);
+    // short file: 3 rows more than the file holds
+    qmf::FactorData c(n + 3, k), d(n + 3, k);
+    c.setFactors([](size_t, size_t) { return 7.0; });
+    d.setFactors([](size_t, size_t) { return 7.0; });
+    c.setFactorsSequential(path);
+    d.setFactors(path);
+    EXPECT(std::memcmp(c.getFactors().data(), d.getFactors().data(), (n + 3) * k * sizeof(double)) == 0);
+    EXPECT(d.at(n + 2, k - 1) == 7.0 && d.at(0, 0) == a.at(0, 0));
     std::remove(path.c_str());
   }
   // averaging order of Metric::compute(labels, scores, parallel)

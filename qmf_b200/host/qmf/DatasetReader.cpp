@@ -143,6 +143,11 @@ bool DatasetReader::parseLine(const char* b, const char* e, DatasetElem& elem) {
   return true;
 }
 
+bool DatasetReader::parseDoubleField(const char* b, const char* e, double& out) {
+  const char* p = b;
+  return parseDouble(p, e, out);
+}
+
 bool DatasetReader::readAllMapped(std::vector<DatasetElem>& dataset) {
   if (fileName_.empty() || touched_) return false;
   const int fd = ::open(fileName_.c_str(), O_RDONLY);

@@ -33,6 +33,9 @@ class DatasetReader {
   // Parses one line [b, e) exactly like sscanf(line, "%lld %lld %lf") == 3 does (same integer
   // clamping, same correctly-rounded double); false if the line does not carry three fields.
   static bool parseLine(const char* b, const char* e, DatasetElem& elem);
+  // The first number of [b, e) exactly like sscanf(line, "%lf") == 1 does (leading white space skipped, same correctly
+  // rounded value, trailing text ignored); false if there is none.  Used by FactorData::setFactors(file).
+  static bool parseDoubleField(const char* b, const char* e, double& out);
 
  private:
   bool readAllMapped(std::vector<DatasetElem>& dataset);

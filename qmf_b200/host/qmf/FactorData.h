@@ -31,25 +31,11 @@ class FactorData {
   void setFactors() { factors_.clear(); }
 
   // one value per line, row-major (idx, factor) order: the --distribution_file of the reference
-  // (qmf/FactorData.h:74-100); a short file leaves the remaining entries untouched
-  void setFactors(const std::string& fileName) {
-    std::ifstream in(fileName);
-    std::string line;
-    size_t count = 0;
-    for (size_t i = 0; i < nelems(); ++i) {
-      for (size_t f = 0; f < nfactors(); ++f) {
-        if (!std::getline(in, line)) {
-          LOG(ERROR) << "read uniform data from " << fileName << " failed.";
-          return;
-        }
-        double v = 0.0;
-        CHECK_EQ(std::sscanf(line.c_str(), "%lf", &v), 1) << "the file format is incorrect: " << line;
-        factors_(i, f) = v;
-        ++count;
-      }
-    }
-    LOG(INFO) << "initialized factor from file size: " << count;
-  }
+  // (qmf/FactorData.h:74-100); a short file leaves the remaining entries untouched.  A regular file is mapped and its
+  // line ranges are parsed on all host threads (at 1 M items x 128 factors the getline + sscanf
+  // loop reads 128 M lines); setFactorsSequential is the reference's loop, kept for streams and as the equality check.
+  void setFactors(const std::string& fileName);
+  void setFactorsSequential(const std::string& fileName);
 
   template <typename Fn>
   void setBiases(Fn fn) {
