@@ -38,3 +38,12 @@ r = subprocess.run(cmd, env=env, capture_output=True, text=True, check=True)
 lines = [l.split("] ", 1)[1] for l in r.stderr.splitlines() if "epoch" in l and ("train loss" in l or "recorded metric" in l)]
 open(os.path.join(out, "ref_log.txt"), "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
+
+# --num_test_users: the reference subsamples the test users with std::shuffle(mt19937(eval_seed)) over an unordered_set's
+# iteration order (qmf/Engine.cpp:35-50); which users are drawn decides the averaged metrics
+for ntu, seed in ((40, 7), (120, 42)):
+    cmd2 = cmd[:-2] + ["--num_test_users=%d" % ntu, "--eval_seed=%d" % seed]
+    r = subprocess.run(cmd2, env=env, capture_output=True, text=True, check=True)
+    lines = [l.split("] ", 1)[1] for l in r.stderr.splitlines() if "recorded metric" in l]
+    open(os.path.join(out, "ref_log_numtest%d_seed%d.txt" % (ntu, seed)), "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[-4:]))

@@ -56,6 +56,24 @@ def test_wals_binary_matches_reference_binary(tmp_path):
         assert line in r.stderr
 
 
+@pytest.mark.parametrize("ntu,seed", [(40, 7), (120, 42)])
+def test_wals_binary_num_test_users_samples_the_reference_users(ntu, seed):
+    """--num_test_users / --eval_seed: the subsample of test users (unordered_set order + std::shuffle(mt19937(seed)),
+    qmf/Engine.cpp:35-50) must be the reference's - the averaged metrics of the reference binary's own run are
+    reproduced to 1e-9 only if the same users are drawn (fixtures: tests/golden/make_cli_golden.py)"""
+    cmd = [os.path.join(BIN, "wals"), "--nepochs=3", "--nfactors=30", "--regularization_lambda=0.05", "--confidence_weight=40",
+           "--nthreads=4", "--train_dataset=" + os.path.join(CLI, "train.txt"), "--test_dataset=" + os.path.join(CLI, "test.txt"),
+           "--distribution_file=" + os.path.join(CLI, "dist.txt"), "--test_avg_metrics=auc,ap,p@10,r@10", "--test_always",
+           "--num_test_users=%d" % ntu, "--eval_seed=%d" % seed]
+    r = subprocess.run(cmd, env=dict(os.environ, QMF_LOG_PRECISION="17"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = {k: v for k, v in log_values(r.stderr).items() if k[0] != "loss"}
+    want = log_values(open(os.path.join(CLI, "ref_log_numtest%d_seed%d.txt" % (ntu, seed))).read())
+    assert set(got) == set(want) and len(want) == 12
+    for key, w in want.items():
+        assert abs(got[key] - w) <= 1e-9 * max(abs(w), 1e-30), (key, got[key], w)
+
+
 def test_wals_default_log_format():
     r = subprocess.run([os.path.join(BIN, "wals"), "--nepochs=1", "--nfactors=8", "--seed=5",
                         "--train_dataset=" + os.path.join(CLI, "train.txt")], capture_output=True, text=True, timeout=300)
