@@ -72,18 +72,19 @@ int qmfb_gram_unpack_dev(void* stream, const double* gram_packed, int k, double*
  *   A = G + sum_s alpha r_s y_s y_s^T + lambda I,  b = sum_s (1 + alpha r_s) y_s,  x = A^{-1} b,
  *   row_loss = sum_s (1 + alpha r_s) + x^T (A - lambda I) x - 2 x^T b.
  * CSR arrays are local to the shard (row_ptr[0] == 0); X row written = row_offset + local row.
- * `order` lists local rows longest-first (any permutation is valid).  `nnz` = row_ptr[nrows] (the host's
- * copy; -1 if unknown): rows are bucketed by length - a half-step of short rows (mean < 1024 signals) runs
- * the warp-specialised kernel (builder warps + two solver groups per SM), long rows two plain CTAs per SM;
- * results do not depend on the choice.  `scratch` is 2 ints
+ * `order` lists local rows longest-first (any permutation is valid; the rows at its head with >= 32768
+ * signals are cut into segments that all CTAs build ahead of the solve - a device-planned work list, so a
+ * blockbuster row is not the tail of the half-step).  `nnz` = row_ptr[nrows] (the host's copy; -1 if
+ * unknown; a hint only).  Results do not depend on the kernel choice below.  `scratch` is 2 ints
  * (scheduler counter, error flag; the call resets both).  loss_sum (device, 1 double) receives
  * the deterministic sum of row_loss.  Asynchronous on `stream`. */
 int qmfb_wals_solve_dev(void* stream, double* X, int64_t ldx, int64_t row_offset, const double* Y, int64_t ldy, int k,
                         const int64_t* row_ptr, const int32_t* col, const double* val, const int32_t* order,
                         int64_t nrows, int64_t nnz, const double* gram_packed, double alpha, double lambda, double* row_loss,
                         double* loss_sum, int32_t* scratch);
-/* Process-wide choice of the row-solve kernel for k <= 128: 0 = by mean row length (default), 1 = the plain
- * kernel (two CTAs per SM), 2 = the warp-specialised kernel.  Same results either way; for tests and
+/* Process-wide choice of the row-solve kernel for k <= 128: 0 = default (the plain kernel: CTA per row, two to
+ * twelve resident CTAs per SM by k), 1 = the plain kernel, 2 = the warp-specialised kernel (one CTA per SM: builder
+ * warps + two solver groups; measured no faster).  Same results either way; for tests and
  * measurements (environment: QMFB_SOLVE=classic|ws). */
 int qmfb_wals_set_solve_kernel(int mode);
 /* Same, with the all-gather of the solved shard FUSED into the kernel: every solved row is also
