@@ -474,7 +474,8 @@ def run_ours(args, cfg, workload):
             e2e_ms = float(t.item()) / args.steps
             e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "nnz/s", "h2d_bytes_per_step": world * ni * k * 8,
                    "d2h_bytes_per_step": (nu + ni) * k * 8 + 8 * world, "ms_per_step": e2e_ms,
-                   "api": "ShardedWals.epoch_host: pinned host factors in/out on every rank (CUDA events, max over ranks)"}
+                   "api": "ShardedWals.epoch_host (one process per GPU over the kernel-level C ABI: qmfb_gram_dev, "
+                          "qmfb_wals_solve_peers_dev): pinned host factors in/out on every rank (CUDA events, max over ranks)"}
             # The same epoch through the engine-level C ABI that `wals --ngpus N` / qmf::WALSEngine bind: ONE process
             # (rank 0) drives all N GPUs with qmfb_wals_sharded_epoch_host while the other ranks sleep on a CPU barrier.
             cpu_group = dist.new_group(backend="gloo")
