@@ -268,3 +268,15 @@ def test_not_spd_flag_is_sticky_and_raised_on_every_rank(tmp_path, oracle_lib):
     mp.spawn(_rank_main_not_spd, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert open(str(tmp_path / ("r%d.txt" % r))).read() == "1 0"
+
+
+def test_powerlaw_degrees_follow_the_stated_law():
+    """rank-size law with exponent 1/1.1, clipped to [1, 1e5], scaled to the requested number of draws, seeded"""
+    from qmf_b200.datagen import powerlaw_degrees
+    d = powerlaw_degrees(200_000, 20_000_000, seed=3)
+    assert d.min() >= 1 and d.max() <= 100_000 and abs(int(d.sum()) - 20_000_000) < 200_000 // 2
+    assert np.array_equal(d, powerlaw_degrees(200_000, 20_000_000, seed=3))
+    s = np.sort(d)[::-1].astype(np.float64)
+    j = np.array([1000, 10_000, 100_000])                     # unclipped part of the law: d(j) ~ j^(-1/1.1)
+    slope = np.polyfit(np.log(j), np.log(s[j - 1]), 1)[0]
+    assert abs(slope + 1 / 1.1) < 0.02, slope
